@@ -1,0 +1,4 @@
+// Oracle build shim: intentionally empty (nothing from this header is used on the sync path).
+#ifndef COS_SHIM_BOOST_SHARED_PTR_HPP_
+#define COS_SHIM_BOOST_SHARED_PTR_HPP_
+#endif
