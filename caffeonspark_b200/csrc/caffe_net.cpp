@@ -1,0 +1,619 @@
+// caffe_net.cpp -- see caffe_net.hpp.
+#include "caffe_net.hpp"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <sstream>
+
+namespace cosb {
+namespace {
+
+std::string rt_err(const char* what, cudaError_t e) {
+  std::ostringstream os;
+  os << what << " failed: " << cudaGetErrorString(e);
+  cudaGetLastError();
+  return os.str();
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define COS_RT(call)                      \
+  do {                                    \
+    cudaError_t e__ = (call);             \
+    if (e__ != cudaSuccess) {             \
+      *err = rt_err(#call, e__);          \
+      return false;                       \
+    }                                     \
+  } while (0)
+
+}  // namespace
+
+// ------------------------------------------------------------------ create
+
+CaffeNet* CaffeNet::create(const SolverSpec& spec, int num_local_devices, int cluster_size, int node_rank,
+                           bool is_training, int connection_type, int start_device_id, std::string* err) {
+  // CaffeNet.cpp:123-124 CHECK_GE(num_local_devices_, 1), CHECK_GE(cluster_size_, 0)
+  if (num_local_devices < 1) {
+    *err = "number of local Devices must be greater than or equal to 1";
+    return nullptr;
+  }
+  if (num_local_devices != 1) {
+    *err = "num_local_devices > 1 inside one executor is not supported yet: run one executor per GPU "
+           "(-devices 1 -clusterSize N)";
+    return nullptr;
+  }
+  if (cluster_size < 1 || cluster_size > kMaxRanks) {
+    *err = "cluster size must be in [1, " + std::to_string(kMaxRanks) + "]";
+    return nullptr;
+  }
+  if (cluster_size == 1) {  // JniCaffeNet.cpp:42-46
+    std::unique_ptr<LocalCaffeNet> n(new LocalCaffeNet(spec, is_training));
+    if (!n->setup(start_device_id, err)) return nullptr;
+    return n.release();
+  }
+  if (node_rank < 0 || node_rank >= cluster_size) {
+    *err = "node_rank out of range";
+    return nullptr;
+  }
+  if (connection_type != COS_CONNECTION_RDMA && connection_type != COS_CONNECTION_SOCKET) {
+    *err = "unable to create CaffeNet object";  // JniCaffeNet.cpp:72-75 (no matching switch case)
+    return nullptr;
+  }
+  std::unique_ptr<NvlinkCaffeNet> n(new NvlinkCaffeNet(spec, cluster_size, node_rank, is_training));
+  if (!n->setup(start_device_id, err)) return nullptr;
+  return n.release();
+}
+
+CaffeNet::CaffeNet(const SolverSpec& spec, int cluster_size, int node_rank, bool is_training)
+    : spec_(spec), world_(cluster_size), rank_(node_rank), is_training_(is_training) {
+  count_ = spec_.param_count();
+  iter_ = spec_.init_iter;
+  if (const char* t = getenv("COS_BARRIER_TIMEOUT_MS")) opt_timeout_ms_ = atoll(t);
+}
+
+CaffeNet::~CaffeNet() {
+  if (device_ >= 0) {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    cudaDeviceSynchronize();
+    for (void* p : in_dev_)
+      if (p) cudaFree(p);
+    if (seg_end_) cudaFree(seg_end_);
+    if (seg_lr_) cudaFree(seg_lr_);
+    if (seg_dm_) cudaFree(seg_dm_);
+    if (loss_dev_) cudaFree(loss_dev_);
+    if (loss_host_) cudaFreeHost(loss_host_);
+    if (status_) cudaFreeHost(status_);
+    if (ev_start_) cudaEventDestroy(ev_start_);
+    if (ev_stop_) cudaEventDestroy(ev_stop_);
+    if (stream_) cudaStreamDestroy(stream_);
+    arena_.destroy();
+    cudaGetLastError();
+  }
+}
+
+// CaffeNet.cpp:130-142: devices are grabbed starting after start_device_id
+// (Caffe::FindDevice picks the first usable one).
+bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::string* err) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    *err = "cannot grab GPU device: " + std::string(e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device") +
+           " (this library has no CPU path)";
+    cudaGetLastError();
+    return false;
+  }
+  int dev = -1;
+  for (int d = start_device_id + 1; d < ndev; ++d) {
+    if (d < 0) continue;
+    if (cudaSetDevice(d) == cudaSuccess && cudaFree(0) == cudaSuccess) {
+      dev = d;
+      break;
+    }
+    cudaGetLastError();
+  }
+  if (dev < 0) {
+    *err = "cannot grab GPU device after id " + std::to_string(start_device_id);
+    return false;
+  }
+  device_ = dev;
+  cudaDeviceProp prop;
+  COS_RT(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) {
+    *err = "device " + std::to_string(dev) + " is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+           "; this library is built for sm_100a (B200) only";
+    return false;
+  }
+
+  // arena = [flags | data_ | diff_ | history | bf16 wire]
+  const size_t fbytes = static_cast<size_t>(count_) * sizeof(float);
+  size_t off = align_up(kFlagBytes, 4096);
+  off_data_ = off;
+  off = align_up(off + fbytes, 4096);
+  off_diff_ = off;
+  off = align_up(off + fbytes, 4096);
+  off_hist_ = off;
+  off = align_up(off + fbytes, 4096);
+  off_wire_ = off;
+  if (spec_.grad_dtype == COS_GRAD_BF16) off = align_up(off + static_cast<size_t>(count_) * 2, 4096);
+  const char* tr = getenv("COS_PEER_TRANSPORT");
+  const bool prefer_vmm = peer_mappable && !(tr && strcmp(tr, "ipc") == 0);
+  if (!arena_.create(dev, off, prefer_vmm, err)) return false;
+  char* base = static_cast<char*>(arena_.base());
+  data_ = reinterpret_cast<float*>(base + off_data_);
+  diff_ = reinterpret_cast<float*>(base + off_diff_);
+  hist_ = reinterpret_cast<float*>(base + off_hist_);
+  wire_ = spec_.grad_dtype == COS_GRAD_BF16 ? reinterpret_cast<uint16_t*>(base + off_wire_) : nullptr;
+  peer_data_[rank_] = data_;
+  peer_diff_[rank_] = diff_;
+  peer_wire_[rank_] = wire_;
+  peer_hist_[rank_] = hist_;
+  peer_flags_[rank_] = reinterpret_cast<uint32_t*>(base);
+
+  // blob (segment) table: cumulative ends + multipliers
+  std::vector<uint64_t> ends;
+  std::vector<float> lr, dm;
+  uint64_t acc = 0;
+  for (size_t k = 0; k < spec_.counts.size(); ++k) {
+    if (spec_.counts[k] < 0) {
+      *err = "negative blob count";
+      return false;
+    }
+    acc += static_cast<uint64_t>(spec_.counts[k]);
+    ends.push_back(acc);
+    lr.push_back(k < spec_.lr_mult.size() ? spec_.lr_mult[k] : 1.0f);
+    dm.push_back(k < spec_.decay_mult.size() ? spec_.decay_mult[k] : 1.0f);
+  }
+  if (ends.empty() || acc == 0) {  // net without learnable parameters: size_ == 1
+    ends.assign(1, 1);
+    lr.assign(1, 1.0f);
+    dm.assign(1, 1.0f);
+  }
+  nseg_ = static_cast<int>(ends.size());
+  COS_RT(cudaMalloc(reinterpret_cast<void**>(&seg_end_), nseg_ * sizeof(uint64_t)));
+  COS_RT(cudaMalloc(reinterpret_cast<void**>(&seg_lr_), nseg_ * sizeof(float)));
+  COS_RT(cudaMalloc(reinterpret_cast<void**>(&seg_dm_), nseg_ * sizeof(float)));
+  COS_RT(cudaMemcpy(seg_end_, ends.data(), nseg_ * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  COS_RT(cudaMemcpy(seg_lr_, lr.data(), nseg_ * sizeof(float), cudaMemcpyHostToDevice));
+  COS_RT(cudaMemcpy(seg_dm_, dm.data(), nseg_ * sizeof(float), cudaMemcpyHostToDevice));
+
+  COS_RT(cudaHostAlloc(reinterpret_cast<void**>(&status_), sizeof(int), cudaHostAllocMapped));
+  *status_ = 0;
+  COS_RT(cudaMalloc(reinterpret_cast<void**>(&loss_dev_), sizeof(float)));
+  COS_RT(cudaMemset(loss_dev_, 0, sizeof(float)));
+  COS_RT(cudaHostAlloc(reinterpret_cast<void**>(&loss_host_), sizeof(float), cudaHostAllocDefault));
+  *loss_host_ = 0.f;
+  COS_RT(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  COS_RT(cudaEventCreate(&ev_start_));
+  COS_RT(cudaEventCreate(&ev_stop_));
+  return true;
+}
+
+int CaffeNet::deviceID(int solver_index) const { return solver_index == 0 ? device_ : -1; }
+
+// CaffeNet.cpp:585-654: per-thread binding to the solver's device.
+bool CaffeNet::init(int solver_index, bool enable_nn, std::string* err) {
+  (void)enable_nn;
+  if (solver_index != 0) {
+    *err = "solver_index must be 0";
+    return false;
+  }
+  COS_RT(cudaSetDevice(device_));
+  return true;
+}
+
+int CaffeNet::resolved_algo() const {
+  if (world_ == 1) return kModeLocal;
+  if (opt_algo_ == COS_ALGO_TWO_SHOT) return kModeTwoShot;
+  if (opt_algo_ == COS_ALGO_ONE_SHOT) return kModeOneShot;
+  return static_cast<int64_t>(count_ * sizeof(float)) <= opt_one_shot_max_bytes_ ? kModeOneShot : kModeTwoShot;
+}
+
+float CaffeNet::current_rate() {
+  int step = current_step_;
+  float r = 0.f;
+  learning_rate(spec_.lr_policy, spec_.base_lr, spec_.gamma, spec_.power, spec_.stepsize,
+                spec_.stepvalues.empty() ? nullptr : spec_.stepvalues.data(),
+                static_cast<int>(spec_.stepvalues.size()), spec_.max_iter, iter_, &step, &r);
+  return r;
+}
+
+bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
+  SyncParams p;
+  memset(&p, 0, sizeof(p));
+  p.world = world_;
+  p.rank = rank_;
+  p.mode = mode;
+  p.grad_bf16 = spec_.grad_dtype == COS_GRAD_BF16;
+  p.zero_diff = opt_zero_diff_;
+  p.nseg = nseg_;
+  p.count = count_;
+  for (int r = 0; r < world_; ++r) {
+    p.data[r] = peer_data_[r];
+    p.diff[r] = peer_diff_[r];
+    p.wire[r] = peer_wire_[r];
+    p.flags[r] = peer_flags_[r];
+  }
+  p.hist = hist_;
+  p.seg_end = seg_end_;
+  p.seg_lr_mult = seg_lr_;
+  p.seg_decay_mult = seg_dm_;
+  p.momentum = spec_.momentum;
+  p.weight_decay = spec_.weight_decay;
+  p.inv_scale = static_cast<float>(1.0 / static_cast<double>(world_));  // Dtype(1.0 / solver_count)
+  p.timeout_ns = static_cast<unsigned long long>(opt_timeout_ms_) * 1000000ull;
+  p.status = status_;
+  if (mode != kModeAllGather) {
+    if (!learning_rate(spec_.lr_policy, spec_.base_lr, spec_.gamma, spec_.power, spec_.stepsize,
+                       spec_.stepvalues.empty() ? nullptr : spec_.stepvalues.data(),
+                       static_cast<int>(spec_.stepvalues.size()), spec_.max_iter, iter_, &current_step_,
+                       &p.rate)) {
+      *err = "Unknown learning rate policy: " + spec_.lr_policy;
+      return false;
+    }
+  }
+  if (world_ > 1) p.epoch = ++epoch_;
+  if (opt_timing_) COS_RT(cudaEventRecord(ev_start_, stream));
+  cudaError_t e = (opt_kernel_ == 1 && mode != kModeAllGather)
+                      ? launch_fused_sync_sgd_tma(p, opt_grid_, stream)
+                      : launch_fused_sync_sgd(p, opt_grid_, opt_block_, stream);
+  if (e != cudaSuccess) {
+    *err = rt_err("fused_sync_sgd launch", e);
+    return false;
+  }
+  if (opt_timing_) {
+    COS_RT(cudaEventRecord(ev_stop_, stream));
+    ev_valid_ = true;
+  }
+  ++launches_;
+  return true;
+}
+
+bool CaffeNet::sync_step(int solver_index, cudaStream_t stream, bool use_own_stream, std::string* err) {
+  if (solver_index != 0) {
+    *err = "solver_index must be 0";
+    return false;
+  }
+  if (world_ > 1 && !connected_) {
+    *err = "solver was not initialized: connect() has not completed";  // CaffeNet.cpp:720
+    return false;
+  }
+  std::lock_guard<std::mutex> g(mu_);
+  COS_RT(cudaSetDevice(device_));
+  if (!launch(resolved_algo(), use_own_stream ? stream_ : stream, err)) return false;
+  ++iter_;  // solver.cpp:257
+  return true;
+}
+
+bool CaffeNet::all_gather_weights(cudaStream_t stream, bool use_own_stream, std::string* err) {
+  if (world_ == 1) return true;
+  if (!connected_) {
+    *err = "connect() has not completed";
+    return false;
+  }
+  std::lock_guard<std::mutex> g(mu_);
+  COS_RT(cudaSetDevice(device_));
+  return launch(kModeAllGather, use_own_stream ? stream_ : stream, err);
+}
+
+bool CaffeNet::check_status(std::string* err) {
+  int s = *reinterpret_cast<volatile int*>(status_);
+  if (s == 0) return true;
+  *reinterpret_cast<volatile int*>(status_) = 0;
+  std::ostringstream os;
+  int which = (s - 100) / 32, peer = (s - 100) % 32;
+  os << "device-side barrier " << (which == 0 ? "A (gradients ready)" : "B (weights landed)") << " timed out after "
+     << opt_timeout_ms_ << " ms waiting for rank " << peer << " (status " << s << ")";
+  *err = os.str();
+  return false;
+}
+
+bool CaffeNet::synchronize(std::string* err) {
+  COS_RT(cudaSetDevice(device_));
+  COS_RT(cudaStreamSynchronize(stream_));
+  COS_RT(cudaDeviceSynchronize());
+  return check_status(err);
+}
+
+float CaffeNet::last_kernel_ms() {
+  if (!ev_valid_) return -1.f;
+  cudaSetDevice(device_);
+  if (cudaEventSynchronize(ev_stop_) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.f;
+  }
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, ev_start_, ev_stop_) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.f;
+  }
+  return ms;
+}
+
+// CaffeNet.cpp:707-729 train(): feed the batch, Solver::Step(1).
+bool CaffeNet::train(int solver_index, const cos_blob* data, int ndata, std::string* err) {
+  if (solver_index != 0) {
+    *err = "solver_index must be 0";
+    return false;
+  }
+  if (!data) {
+    *err = "data is NULL";  // JniCaffeNet.cpp:391-395
+    return false;
+  }
+  if (!fb_fn_) {
+    *err = "train: no gradient producer registered (cos_net_set_forward_backward); Net::ForwardBackward is "
+           "outside this library";
+    return false;
+  }
+  COS_RT(cudaSetDevice(device_));
+  // MemoryInputAdapter::feed (MemoryInputAdapter.cpp:24-32) equivalent: stage host blobs on the device
+  if (static_cast<int>(in_dev_.size()) < ndata) {
+    in_dev_.resize(ndata, nullptr);
+    in_bytes_.resize(ndata, 0);
+  }
+  std::vector<cos_blob> dev_blobs(ndata);
+  for (int i = 0; i < ndata; ++i) {
+    if (!data[i].data) {
+      *err = "data[" + std::to_string(i) + "] is NULL";
+      return false;
+    }
+    size_t n = static_cast<size_t>(data[i].num) * data[i].channels * data[i].height * data[i].width * sizeof(float);
+    if (n > in_bytes_[i]) {
+      if (in_dev_[i]) cudaFree(in_dev_[i]);
+      in_dev_[i] = nullptr;
+      COS_RT(cudaMalloc(&in_dev_[i], n));
+      in_bytes_[i] = n;
+    }
+    COS_RT(cudaMemcpyAsync(in_dev_[i], data[i].data, n, cudaMemcpyHostToDevice, stream_));
+    dev_blobs[i] = data[i];
+    dev_blobs[i].data = static_cast<const float*>(in_dev_[i]);
+  }
+  int rc = fb_fn_(fb_user_, solver_index, dev_blobs.data(), ndata, loss_dev_, stream_);
+  if (rc != 0) {
+    *err = "gradient producer failed with code " + std::to_string(rc);
+    return false;
+  }
+  if (!sync_step(solver_index, stream_, true, err)) return false;
+  COS_RT(cudaMemcpyAsync(loss_host_, loss_dev_, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+  COS_RT(cudaStreamSynchronize(stream_));
+  last_loss_ = *loss_host_;
+  return check_status(err);
+}
+
+bool CaffeNet::set_option(const std::string& name, int64_t v, std::string* err) {
+  if (name == "algo") {
+    if (v < 0 || v > 2) { *err = "algo must be 0..2"; return false; }
+    opt_algo_ = static_cast<int>(v);
+  } else if (name == "zero_diff") opt_zero_diff_ = v != 0;
+  else if (name == "grid") opt_grid_ = static_cast<int>(v);
+  else if (name == "block") opt_block_ = static_cast<int>(v);
+  else if (name == "kernel") opt_kernel_ = static_cast<int>(v);
+  else if (name == "timing") opt_timing_ = v != 0;
+  else if (name == "nvls") opt_nvls_ = v != 0;
+  else if (name == "barrier_timeout_ms") opt_timeout_ms_ = v;
+  else if (name == "one_shot_max_bytes") opt_one_shot_max_bytes_ = v;
+  else if (name == "iter") { iter_ = static_cast<int>(v); }
+  else {
+    *err = "unknown option '" + name + "'";
+    return false;
+  }
+  return true;
+}
+
+int64_t CaffeNet::get_option(const std::string& name) const {
+  if (name == "algo") return opt_algo_;
+  if (name == "resolved_algo") return resolved_algo();
+  if (name == "zero_diff") return opt_zero_diff_;
+  if (name == "grid") return opt_grid_;
+  if (name == "block") return opt_block_;
+  if (name == "kernel") return opt_kernel_;
+  if (name == "timing") return opt_timing_;
+  if (name == "nvls") return opt_nvls_;
+  if (name == "barrier_timeout_ms") return opt_timeout_ms_;
+  if (name == "one_shot_max_bytes") return opt_one_shot_max_bytes_;
+  if (name == "transport") return arena_.transport();
+  if (name == "default_grid") return default_sync_grid(device_);
+  return -1;
+}
+
+// ---------------------------------------------------------------- snapshot
+// Flat little-endian files: header {magic, version, iter, current_step, count,
+// nblobs, counts[nblobs]} + fp32 payload.  Rank 0 is the only caller in the
+// reference (CaffeProcessor.scala:454-465); its weights are globally
+// consistent here (the kernel all-gathers every step), and the history of the
+// other shards is read straight from the owners' arenas over NVLink, which
+// removes the reference's stale-shard quirks.
+namespace {
+bool write_flat(const std::string& path, const char* magic, int iter, int current_step, const SolverSpec& spec,
+                uint64_t count, const std::vector<float>& payload, std::string* err) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) {
+    *err = "cannot open '" + path + "' for writing";
+    return false;
+  }
+  int32_t hdr[4] = {1, iter, current_step, static_cast<int32_t>(spec.counts.size())};
+  bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(&count, 8, 1, f) == 1;
+  for (int64_t c : spec.counts) ok = ok && fwrite(&c, 8, 1, f) == 1;
+  ok = ok && fwrite(payload.data(), sizeof(float), payload.size(), f) == payload.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) *err = "short write to '" + path + "'";
+  return ok;
+}
+}  // namespace
+
+int CaffeNet::snapshot(std::string* err) {
+  std::lock_guard<std::mutex> g(mu_);
+  if (cudaSetDevice(device_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess) {
+    *err = rt_err("snapshot: device sync", cudaGetLastError());
+    return -1;
+  }
+  if (!check_status(err)) return -1;
+  std::vector<float> w(count_), h(count_);
+  cudaError_t e = cudaMemcpy(w.data(), data_, count_ * sizeof(float), cudaMemcpyDeviceToHost);
+  const bool sharded_hist = world_ > 1 && resolved_algo() == kModeTwoShot;
+  for (int r = 0; r < world_ && e == cudaSuccess; ++r) {
+    uint64_t offs = 0, size = count_;
+    if (sharded_hist) chunk(count_, world_, r, &offs, &size);
+    else if (r != rank_) continue;
+    const float* src = (sharded_hist ? peer_hist_[r] : hist_);
+    if (!src) {
+      *err = "snapshot: history of rank " + std::to_string(r) + " is not mapped (connect() first)";
+      return -1;
+    }
+    if (size) e = cudaMemcpy(h.data() + offs, src + offs, size * sizeof(float), cudaMemcpyDeviceToHost);
+  }
+  if (e != cudaSuccess) {
+    *err = rt_err("snapshot: copy to host", e);
+    return -1;
+  }
+  const std::string prefix = spec_.snapshot_prefix.empty() ? std::string("cos_b200") : spec_.snapshot_prefix;
+  const std::string stem = prefix + "_iter_" + std::to_string(iter_);
+  if (!write_flat(stem + ".cosmodel", "COSB2MDL", iter_, current_step_, spec_, count_, w, err)) return -1;
+  if (!write_flat(stem + ".cosstate", "COSB2STA", iter_, current_step_, spec_, count_, h, err)) return -1;
+  return iter_;
+}
+
+bool CaffeNet::restore(const std::string& model_file, const std::string& state_file, std::string* err) {
+  auto read_flat = [&](const std::string& path, const char* magic, std::vector<float>* out, int* iter,
+                       int* step) -> bool {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) {
+      *err = "cannot open '" + path + "'";
+      return false;
+    }
+    char m[8];
+    int32_t hdr[4];
+    uint64_t count = 0;
+    bool ok = fread(m, 1, 8, f) == 8 && memcmp(m, magic, 8) == 0 && fread(hdr, sizeof(hdr), 1, f) == 1 &&
+              fread(&count, 8, 1, f) == 1 && hdr[0] == 1 && count == count_;
+    if (ok) ok = fseek(f, static_cast<long>(hdr[3]) * 8, SEEK_CUR) == 0;
+    if (ok) {
+      out->resize(count);
+      ok = fread(out->data(), sizeof(float), count, f) == count;
+      *iter = hdr[1];
+      *step = hdr[2];
+    }
+    fclose(f);
+    if (!ok) *err = "'" + path + "' is not a matching snapshot of this net";
+    return ok;
+  };
+  COS_RT(cudaSetDevice(device_));
+  int it = 0, st = 0;
+  std::vector<float> buf;
+  if (!model_file.empty()) {
+    if (!read_flat(model_file, "COSB2MDL", &buf, &it, &st)) return false;
+    COS_RT(cudaMemcpy(data_, buf.data(), count_ * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (!state_file.empty()) {  // CaffeNet.cpp:198-203: Restore() also resumes iter_
+    if (!read_flat(state_file, "COSB2STA", &buf, &it, &st)) return false;
+    COS_RT(cudaMemcpy(hist_, buf.data(), count_ * sizeof(float), cudaMemcpyHostToDevice));
+    iter_ = it;
+    current_step_ = st;
+    spec_.init_iter = it;
+  }
+  return true;
+}
+
+// ----------------------------------------------------------- NvlinkCaffeNet
+
+NvlinkCaffeNet::NvlinkCaffeNet(const SolverSpec& spec, int cluster_size, int node_rank, bool is_training)
+    : CaffeNet(spec, cluster_size, node_rank, is_training) {}
+
+NvlinkCaffeNet::~NvlinkCaffeNet() {
+  if (device_ >= 0) {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    cudaDeviceSynchronize();
+    cudaGetLastError();
+  }
+  // Peers may still be inside a kernel that touches this arena: give them a
+  // short rendezvous.  (The physical allocation is reference-counted by the
+  // importers, so a peer that is late still never faults.)
+  if (connected_ && adapter_) {
+    std::string ignore;
+    adapter_->barrier(2000, &ignore);
+  }
+  mappings_.clear();
+  adapter_.reset();
+}
+
+bool NvlinkCaffeNet::setup(int start_device_id, std::string* err) {
+  if (!allocate_device(start_device_id, true, err)) return false;
+  // CaffeNet.cpp:253-272: adapter (listener) first, then one channel per peer
+  adapter_.reset(new PeerAdapter(world_, rank_));
+  if (!adapter_->ok()) {
+    *err = "peer adapter: " + adapter_->init_error();
+    return false;
+  }
+  ArenaMeta m = arena_.meta();
+  adapter_->offer("arena", arena_.fd(), std::string(reinterpret_cast<const char*>(&m), sizeof(m)));
+  mappings_.resize(world_);
+  return true;
+}
+
+void NvlinkCaffeNet::localAddresses(std::vector<std::string>* vec) {
+  vec->assign(world_, std::string());
+  for (int i = 0; i < world_; ++i)
+    if (i != rank_) (*vec)[i] = adapter_->address();  // "" at the own rank (CaffeNet.cpp:398-401)
+}
+
+bool NvlinkCaffeNet::connect(const std::vector<std::string>& addresses, std::string* err) {
+  if (connected_) return true;
+  if (static_cast<int>(addresses.size()) < world_) {
+    *err = "connect: need " + std::to_string(world_) + " addresses, got " + std::to_string(addresses.size());
+    return false;
+  }
+  COS_RT(cudaSetDevice(device_));
+  if (!adapter_->connect(addresses, err)) return false;
+  const int timeout = static_cast<int>(opt_timeout_ms_);
+  for (int n = 1; n < world_; ++n) {
+    const int peer = (rank_ + n) % world_;
+    int fd = -1;
+    std::string meta;
+    if (!adapter_->fetch(peer, "arena", &fd, &meta, timeout, err)) return false;
+    if (meta.size() != sizeof(ArenaMeta)) {
+      if (fd >= 0) close(fd);
+      *err = "connect: bad arena metadata from rank " + std::to_string(peer);
+      return false;
+    }
+    ArenaMeta m;
+    memcpy(&m, meta.data(), sizeof(m));
+    if (m.bytes != arena_.bytes()) {
+      if (fd >= 0) close(fd);
+      *err = "connect: rank " + std::to_string(peer) + " has a different parameter layout (arena " +
+             std::to_string(m.bytes) + " vs " + std::to_string(arena_.bytes()) + " bytes)";
+      return false;
+    }
+    mappings_[peer].reset(new PeerMapping());
+    if (!mappings_[peer]->open(m, fd, device_, err)) {
+      *err = "connect: mapping rank " + std::to_string(peer) + "'s arena: " + *err;
+      return false;
+    }
+    char* base = static_cast<char*>(mappings_[peer]->base());
+    peer_flags_[peer] = reinterpret_cast<uint32_t*>(base);
+    peer_data_[peer] = reinterpret_cast<float*>(base + off_data_);
+    peer_diff_[peer] = reinterpret_cast<const float*>(base + off_diff_);
+    peer_hist_[peer] = reinterpret_cast<const float*>(base + off_hist_);
+    peer_wire_[peer] = wire_ ? reinterpret_cast<uint16_t*>(base + off_wire_) : nullptr;
+  }
+  connected_ = true;
+  // everyone has mapped everyone; then the first on_start(): all-gather of the
+  // owners' weight shards (socket_sync_cpu.cpp:102-105), so that all ranks
+  // start from the same weights even if they were initialised differently.
+  if (!adapter_->barrier(timeout, err)) return false;
+  if (!all_gather_weights(nullptr, true, err)) return false;
+  if (!synchronize(err)) return false;
+  if (!adapter_->barrier(timeout, err)) return false;
+  return true;
+}
+
+bool NvlinkCaffeNet::sync(std::string* err) {
+  if (world_ > 1) return adapter_->barrier(static_cast<int>(opt_timeout_ms_), err);
+  return true;
+}
+
+}  // namespace cosb

@@ -1,0 +1,164 @@
+// caffe_net.hpp -- object model behind the C ABI.
+//
+// Mirrors caffe-distri/include/CaffeNet.hpp:18-350 for the sync path:
+//   CaffeNet        (base: solver spec, flat Params buffers, iteration state)
+//   LocalCaffeNet   (cluster_size == 1: fused SGD only)            CaffeNet.hpp:163-203
+//   NvlinkCaffeNet  (cluster_size  > 1: stands in for BOTH SocketCaffeNet
+//                    CaffeNet.hpp:263-313 and RDMACaffeNet :206-260 -- the
+//                    transport is NVLink peer memory instead of TCP / verbs)
+// Method names follow the reference (localAddresses, connect, sync, deviceID,
+// init, train, snapshot, getInitIter, getMaxIter, getTestIter,
+// getTestInterval).
+#ifndef COS_CAFFE_NET_HPP_
+#define COS_CAFFE_NET_HPP_
+
+#include <cuda_runtime_api.h>
+
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/caffedistri_b200.h"
+#include "fused_sync_sgd.hpp"
+#include "peer_adapter.hpp"
+#include "peer_memory.hpp"
+#include "solver_spec.hpp"
+
+namespace cosb {
+
+class CaffeNet {
+ public:
+  // JniCaffeNet.cpp:41-64 dispatch.  Returns nullptr and sets *err on failure.
+  static CaffeNet* create(const SolverSpec& spec, int num_local_devices, int cluster_size, int node_rank,
+                          bool is_training, int connection_type, int start_device_id, std::string* err);
+  virtual ~CaffeNet();
+
+  virtual void localAddresses(std::vector<std::string>* vec) = 0;
+  virtual bool connect(const std::vector<std::string>& addresses, std::string* err) = 0;
+  virtual bool sync(std::string* err) { (void)err; return true; }  // CaffeNet.hpp:91
+
+  int deviceID(int solver_index) const;
+  bool init(int solver_index, bool enable_nn, std::string* err);
+  bool train(int solver_index, const cos_blob* data, int ndata, std::string* err);
+  int snapshot(std::string* err);
+  // resume from files written by snapshot() (CaffeNet.cpp:198-205 restore path)
+  bool restore(const std::string& model_file, const std::string& state_file, std::string* err);
+  int getInitIter(int solver_index) const { return solver_index == 0 ? spec_.init_iter : -1; }
+  int getMaxIter(int solver_index) const { return solver_index == 0 ? spec_.max_iter : -1; }
+  int getTestIter(int solver_index) const { return solver_index == 0 ? spec_.test_iter : -1; }
+  int getTestInterval() const { return spec_.test_interval; }
+
+  // hot path
+  bool sync_step(int solver_index, cudaStream_t stream, bool use_own_stream, std::string* err);
+  bool all_gather_weights(cudaStream_t stream, bool use_own_stream, std::string* err);
+  bool synchronize(std::string* err);
+
+  void set_forward_backward(cos_forward_backward_fn fn, void* user) { fb_fn_ = fn; fb_user_ = user; }
+  float* data() const { return data_; }
+  float* diff() const { return diff_; }
+  float* history() const { return hist_; }
+  uint64_t param_count() const { return count_; }
+  int cluster_size() const { return world_; }
+  int rank() const { return rank_; }
+  int iter() const { return iter_; }
+  float current_rate();
+  float last_loss() const { return last_loss_; }
+  float last_kernel_ms();
+  int64_t launch_count() const { return launches_; }
+  bool set_option(const std::string& name, int64_t v, std::string* err);
+  int64_t get_option(const std::string& name) const;
+  const SolverSpec& spec() const { return spec_; }
+  const std::vector<const char*>& address_cstrs() { return addr_cstrs_; }
+  std::vector<std::string>& address_store() { return addr_store_; }
+
+ protected:
+  CaffeNet(const SolverSpec& spec, int cluster_size, int node_rank, bool is_training);
+  bool allocate_device(int start_device_id, bool peer_mappable, std::string* err);
+  bool launch(int mode, cudaStream_t stream, std::string* err);
+  bool check_status(std::string* err);
+  int resolved_algo() const;
+
+  SolverSpec spec_;
+  const int world_;
+  const int rank_;
+  const bool is_training_;
+  int device_ = -1;
+  uint64_t count_ = 0;
+
+  // Params<Dtype> (parallel.hpp:22-45): flat buffers, inside the peer-mappable arena
+  DeviceArena arena_;
+  size_t off_data_ = 0, off_diff_ = 0, off_hist_ = 0, off_wire_ = 0;
+  float* data_ = nullptr;
+  float* diff_ = nullptr;
+  uint16_t* wire_ = nullptr;
+  float* hist_ = nullptr;          // SGDSolver::history_ (sgd_solver.cpp:66-78); in the arena so that a
+                                   // snapshot on rank 0 can read the owners' shards
+  uint64_t* seg_end_ = nullptr;    // device copies of the blob table
+  float* seg_lr_ = nullptr;
+  float* seg_dm_ = nullptr;
+  int nseg_ = 0;
+  int* status_ = nullptr;          // pinned + mapped: device-side error word
+  float* loss_dev_ = nullptr;
+  float* loss_host_ = nullptr;     // pinned
+
+  // pointer tables for the kernel ([rank_] = local)
+  float* peer_data_[kMaxRanks] = {};
+  const float* peer_diff_[kMaxRanks] = {};
+  uint16_t* peer_wire_[kMaxRanks] = {};
+  const float* peer_hist_[kMaxRanks] = {};
+  uint32_t* peer_flags_[kMaxRanks] = {};
+  bool connected_ = false;
+
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_start_ = nullptr, ev_stop_ = nullptr;
+  bool ev_valid_ = false;
+  int iter_ = 0;
+  int current_step_ = 0;  // SGDSolver::current_step_
+  uint32_t epoch_ = 0;
+  int64_t launches_ = 0;
+  float last_loss_ = 0.f;
+
+  // options
+  int opt_algo_ = COS_ALGO_AUTO;
+  int opt_zero_diff_ = 1;
+  int opt_grid_ = 0, opt_block_ = 0;
+  int opt_kernel_ = 0;
+  int opt_timing_ = 1;
+  int opt_nvls_ = 0;
+  int64_t opt_timeout_ms_ = 20000;
+  int64_t opt_one_shot_max_bytes_ = 256 << 10;
+
+  cos_forward_backward_fn fb_fn_ = nullptr;
+  void* fb_user_ = nullptr;
+  std::vector<void*> in_dev_;       // staged input blobs
+  std::vector<size_t> in_bytes_;
+  std::vector<std::string> addr_store_;
+  std::vector<const char*> addr_cstrs_;
+  std::mutex mu_;
+};
+
+class LocalCaffeNet : public CaffeNet {
+ public:
+  LocalCaffeNet(const SolverSpec& spec, bool is_training) : CaffeNet(spec, 1, 0, is_training) {}
+  bool setup(int start_device_id, std::string* err) { return allocate_device(start_device_id, false, err); }
+  void localAddresses(std::vector<std::string>* vec) override { vec->clear(); }  // CaffeNet.cpp:376-378
+  bool connect(const std::vector<std::string>&, std::string*) override { connected_ = true; return true; }
+};
+
+class NvlinkCaffeNet : public CaffeNet {
+ public:
+  NvlinkCaffeNet(const SolverSpec& spec, int cluster_size, int node_rank, bool is_training);
+  ~NvlinkCaffeNet() override;
+  bool setup(int start_device_id, std::string* err);
+  void localAddresses(std::vector<std::string>* vec) override;  // CaffeNet.cpp:394-404
+  bool connect(const std::vector<std::string>& addresses, std::string* err) override;  // :456-480
+  bool sync(std::string* err) override;  // :497-504
+
+ private:
+  std::unique_ptr<PeerAdapter> adapter_;
+  std::vector<std::unique_ptr<PeerMapping>> mappings_;
+};
+
+}  // namespace cosb
+#endif

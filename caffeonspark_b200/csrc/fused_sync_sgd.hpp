@@ -1,0 +1,64 @@
+// fused_sync_sgd.hpp -- launch interface of the hot-path kernels.
+//
+// One launch performs what the reference spreads over on_gradients_ready()
+// (parallel_cpu.cpp:120-122 scale, socket_sync_cpu.cpp:108-133 reduce-scatter),
+// SGDSolver::ApplyUpdate (sgd_solver.cpp:102-116) and the next Step's
+// on_start() (socket_sync_cpu.cpp:102-105 all-gather), see fused_sync_sgd.cu.
+#ifndef COS_FUSED_SYNC_SGD_HPP_
+#define COS_FUSED_SYNC_SGD_HPP_
+
+#include <cuda_runtime_api.h>
+#include <stdint.h>
+
+namespace cosb {
+
+constexpr int kMaxRanks = 16;
+constexpr int kMaxCtas = 2048;
+// Flag region at the start of every rank's arena: two arrays [kMaxCtas][kMaxRanks]
+// of 32-bit epochs (A = "gradients ready", B = "reads done + weights landed").
+constexpr size_t kFlagBytes = 2ull * kMaxCtas * kMaxRanks * sizeof(uint32_t);
+
+enum SyncMode : int {
+  kModeLocal = 0,      // world == 1: fused SGD only
+  kModeTwoShot = 1,    // reduce-scatter -> SGD on owned shard -> weight push
+  kModeOneShot = 2,    // every rank reduces and updates everything, no push
+  kModeAllGather = 3,  // on_start() alone: push owned weight shard to peers
+};
+
+struct SyncParams {
+  int world;
+  int rank;
+  int mode;
+  int grad_bf16;   // reduce over the bf16 wire buffers (cast fused in phase 0)
+  int zero_diff;   // fold the next Step's ClearParamDiffs into the kernel
+  int nseg;
+  uint64_t count;  // P: fp32 elements in data_/diff_/history
+  float* data[kMaxRanks];           // data_ of every rank ([rank] is local)
+  const float* diff[kMaxRanks];     // diff_ of every rank (fp32)
+  uint16_t* wire[kMaxRanks];        // bf16 gradient wire buffer of every rank
+  uint32_t* flags[kMaxRanks];       // flag region of every rank
+  float* hist;                      // local SGD history (momentum buffer)
+  const uint64_t* seg_end;          // [nseg] cumulative blob ends (exclusive)
+  const float* seg_lr_mult;         // [nseg]
+  const float* seg_decay_mult;      // [nseg]
+  float rate;                       // GetLearningRate() of this iteration
+  float momentum;
+  float weight_decay;
+  float inv_scale;                  // (float)(1.0 / solver_count)
+  uint32_t epoch;                   // barrier epoch of this launch
+  unsigned long long timeout_ns;    // barrier time-out
+  int* status;                      // local device word: 0 ok, else error code
+};
+
+// Launches the vector (LDG/STG) kernel.  grid/block 0 = defaults.
+cudaError_t launch_fused_sync_sgd(const SyncParams& p, int grid, int block, cudaStream_t stream);
+// Launches the TMA (cp.async.bulk) pipelined variant of the same computation.
+cudaError_t launch_fused_sync_sgd_tma(const SyncParams& p, int grid, cudaStream_t stream);
+// Occupancy-derived default grid (co-resident CTAs) for the vector kernel.
+int default_sync_grid(int device);
+// Device-side synthetic fill, identical to cos_oracle_fill (tests/bench).
+cudaError_t launch_fill(float* out, uint64_t n, uint64_t seed, uint64_t stream_id, float amp,
+                        cudaStream_t stream);
+
+}  // namespace cosb
+#endif

@@ -1,0 +1,154 @@
+"""CPU tests of the product library's host side: the C ABI loads and exports
+every symbol include/caffedistri_b200.h declares, the pure host functions
+(chunk, learning rate, prototxt layout parser) agree with the oracle / the
+reference's config files, and compute entry points FAIL LOUDLY without a GPU.
+No device compute is attempted here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, gpu_count
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "caffedistri_b200.h")).read()
+    return sorted(set(re.findall(r"COS_API[^;(]*?\b(cos_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(cos):
+    from caffeonspark_b200 import _lib
+    names = _header_symbols()
+    assert len(names) >= 40
+    L = ctypes.CDLL(cos.library_path())
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    bound = {s[0] for s in _lib.SYMBOLS}
+    assert set(names) == bound, f"ctypes table out of sync with the header: {set(names) ^ bound}"
+    assert b"sm_100a" in _lib.lib().cos_version()
+
+
+def test_no_libcuda_link_dependency(cos):
+    # the library must load on a GPU-less box: driver API only via cudaGetDriverEntryPoint
+    import subprocess
+    out = subprocess.run(["ldd", cos.library_path()], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libnccl" not in out
+
+
+def test_chunk_matches_oracle_bit_exact(cos, oracle):
+    rng = np.random.RandomState(5)
+    cases = [(431080, 8), (145578, 4), (60965224, 8), (1, 2), (5, 8), (2 ** 33 + 7, 7)]
+    cases += [(int(rng.randint(1, 10 ** 9)), int(rng.randint(1, 17))) for _ in range(200)]
+    for P, N in cases:
+        for r in range(N):
+            assert cos.chunk(P, N, r) == oracle.chunk(P, N, r)
+
+
+def test_learning_rate_matches_oracle_bit_exact(cos, oracle):
+    pol = [("fixed", {}), ("inv", dict(gamma=1e-4, power=0.75)), ("step", dict(gamma=0.1, stepsize=7)),
+           ("exp", dict(gamma=0.999)), ("poly", dict(power=1.5, max_iter=500)),
+           ("sigmoid", dict(gamma=-0.01, stepsize=200)), ("multistep", dict(gamma=0.5, stepvalues=(3, 50, 400)))]
+    for name, kw in pol:
+        st = oracle.LrState()
+        step = 0
+        for it in list(range(0, 60)) + [399, 400, 401, 499]:
+            want = oracle.learning_rate(name, 0.01, it=it, state=st, **kw)
+            got, step = cos.learning_rate(name, 0.01, it=it, current_step=step, **kw)
+            assert np.float32(got).tobytes() == np.float32(want).tobytes(), (name, it, got, want)
+    with pytest.raises(cos.CosError):
+        cos.learning_rate("bogus", 0.1)
+
+
+def test_layout_parser_on_generated_prototxt(cos, tmp_path):
+    from caffeonspark_b200 import nets
+    for name, P in nets.EXPECTED_PARAM_COUNT.items():
+        solver = nets.write_prototxts(name, str(tmp_path))
+        d = cos.parse_solver(solver)
+        counts, lm, dm, _ = nets.layout(name)
+        assert d.counts == counts and d.lr_mult == lm and d.decay_mult == dm
+        assert d.param_count == P
+        s = nets.NETS[name]["solver"]
+        assert d.lr_policy == s["lr_policy"] and d.max_iter == s["max_iter"]
+        assert d.base_lr == pytest.approx(s["base_lr"]) and d.momentum == pytest.approx(s["momentum"])
+        assert d.batch_size == nets.NETS[name]["batch"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="reference tree not on this box")
+def test_layout_parser_on_reference_config_files(cos):
+    # the reference's own prototxts must yield these layouts
+    want = {"lenet_memory_solver.prototxt": (431080, 8, "inv", 64),
+            "cifar10_quick_solver.prototxt": (145578, 10, "fixed", 100),
+            "bvlc_reference_solver.prototxt": (60965224, 16, "step", 2),
+            "lenet_cos_solver.prototxt": (431080, 8, None, None)}
+    for f, (P, nblobs, pol, batch) in want.items():
+        d = cos.parse_solver("/root/reference/data/" + f)
+        assert d.param_count == P and len(d.counts) == nblobs
+        if pol:
+            assert d.lr_policy == pol and d.batch_size == batch
+    d = cos.parse_solver("/root/reference/data/bvlc_reference_solver.prototxt")
+    assert d.decay_mult[1::2] == [0.0] * 8 and d.lr_mult[1::2] == [2.0] * 8  # biases: lr 2, decay 0
+
+
+def test_parser_rejects_what_is_off_the_path(cos, tmp_path):
+    p = tmp_path / "s.prototxt"
+    p.write_text('net: "nope.prototxt"\nbase_lr: 0.1\nlr_policy: "fixed"\n')
+    with pytest.raises(cos.CosError, match="cannot read net file"):
+        cos.parse_solver(str(p))
+    p.write_text('type: "Adam"\nbase_lr: 0.1\nlr_policy: "fixed"\nnet_param { }\n')
+    with pytest.raises(cos.CosError, match="only SGD"):
+        cos.parse_solver(str(p))
+    p.write_text('base_lr: 0.1 lr_policy: "fixed" net_param { layer { name: "x" type: "LSTM" bottom: "a" top: "b" } }')
+    with pytest.raises(cos.CosError, match="not understood"):
+        cos.parse_solver(str(p))
+    with pytest.raises(cos.CosError, match="cannot read solver file"):
+        cos.parse_solver(str(tmp_path / "missing.prototxt"))
+
+
+@pytest.mark.skipif(gpu_count() > 0, reason="only meaningful on a GPU-less box")
+def test_compute_fails_loudly_without_a_gpu(cos):
+    d = cos.SolverDesc([100], lr_policy="fixed", base_lr=0.1)
+    with pytest.raises(cos.CosError, match="no CPU path"):
+        cos.CaffeNet(d)
+
+
+def test_adapter_rejects_bogus_addresses(cos):
+    # CaffeNetTest.connectbogus: {"0x222","0x333"} must not connect
+    a = cos.PeerAdapter(2, 0)
+    try:
+        assert a.address().startswith("cosb200://")
+        assert not a.connect(["0x222", "0x333"])
+        assert not a.connect(["", "cosb200://1/cosb200-1-r1-deadbeefdeadbeef"])  # well-formed, nobody listening
+    finally:
+        a.close()
+
+
+def test_adapter_loopback_two_ranks_in_process(cos):
+    # two adapters in one process: connect, CTRL barrier, fd + metadata passing
+    import threading
+    ads = [cos.PeerAdapter(2, r) for r in range(2)]
+    addrs = [a.address() for a in ads]
+    res = [None, None]
+
+    def run(r):
+        ok = ads[r].connect(addrs)
+        ok = ok and ads[r].barrier(5000)
+        res[r] = ok
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert res == [True, True]
+    fd = os.memfd_create("cos_test")
+    os.write(fd, b"hello peer memory")
+    assert ads[0].offer_fd("blob", fd, b"meta-bytes")
+    got, meta = ads[1].fetch_fd(0, "blob")
+    assert got >= 0 and meta.startswith(b"meta-bytes")
+    os.lseek(got, 0, os.SEEK_SET)
+    assert os.read(got, 64) == b"hello peer memory"
+    os.close(got)
+    os.close(fd)
+    with pytest.raises(cos.CosError, match="not offered"):
+        ads[1].fetch_fd(0, "never-offered", timeout_ms=200)
+    [a.close() for a in ads]
