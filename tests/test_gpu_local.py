@@ -1,0 +1,145 @@
+"""-m gpu parity: the fused SGD update at cluster_size == 1 (LocalCaffeNet) vs
+the oracle, through the C ABI.  Bar: BIT-EXACT (the kernel uses explicitly
+rounded, un-fused fp32 ops in the reference's order); the north-star tolerance
+(1e-5 relative) is asserted as well so a failure reads in those terms."""
+import numpy as np
+import pytest
+
+from gpu_util import Ranks, assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+HP_LENET = dict(lr_policy="inv", base_lr=0.01, gamma=0.0001, power=0.75, momentum=0.9, weight_decay=0.0005)
+HP_CIFAR = dict(lr_policy="fixed", base_lr=0.001, momentum=0.9, weight_decay=0.004)
+
+LAYOUTS = {
+    "lenet": ([500, 20, 25000, 50, 400000, 500, 5000, 10], [1, 2] * 4, [1, 1] * 4, HP_LENET),
+    "cifar10_quick": ([2400, 32, 25600, 32, 51200, 64, 65536, 64, 640, 10], [1, 2] * 5, [1, 1] * 5, HP_CIFAR),
+    "ragged_tiny_blobs": ([3, 1, 2, 5, 1, 1, 7, 1021, 2, 1], [1, 2, 1, 2, 1, 2, 1, 2, 1, 2],
+                          [1, 0, 1, 0, 1, 0, 1, 1, 0, 1], HP_LENET),
+    "single_element": ([1], [1], [1], HP_CIFAR),
+    "not_multiple_of_4": ([4099], [1], [1], dict(lr_policy="step", base_lr=0.01, gamma=0.1, stepsize=2,
+                                                 momentum=0.9, weight_decay=0.0005)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LAYOUTS))
+@pytest.mark.parametrize("bf16", [False, True])
+def test_local_update_bit_exact(cos, oracle, name, bf16):
+    counts, lm, dm, hp = LAYOUTS[name]
+    desc = cos.SolverDesc(counts, lm, dm, grad_dtype="bf16" if bf16 else "fp32", **hp)
+    sim = oracle.Simulation(1, counts, lm, dm, seed=7, bf16=bf16, **hp)
+    R = Ranks(cos, desc, 1)
+    try:
+        R.set_weights([sim.data[0]])
+        R.connect()
+        for t in range(5):
+            g = oracle.fill(sim.P, 7, (t + 1) * 4096, 0.01)  # raw fp32 gradient; bf16 rounding happens in-kernel
+            rate = sim.step([sim.gradient(0, t)])
+            assert np.float32(R.nets[0].learning_rate()).tobytes() == np.float32(rate).tobytes()
+            R.step([g])
+            assert R.nets[0].iter() == sim.iter
+            w, h = R.weights(0), R.history(0)
+            assert np.allclose(w, sim.data[0], rtol=1e-5, atol=0)
+            assert_bits_equal(w, sim.data[0], f"{name} weights iter {t}")
+            assert_bits_equal(h, sim.hist[0], f"{name} history iter {t}")
+            assert not R.diff(0).any(), "ClearParamDiffs fold: diff_ must be zero after the step"
+    finally:
+        R.close()
+
+
+def test_zero_diff_can_be_disabled(cos, oracle):
+    counts = [1000, 24]
+    desc = cos.SolverDesc(counts, **HP_CIFAR)
+    R = Ranks(cos, desc, 1, zero_diff=0)
+    try:
+        R.connect()
+        g = oracle.fill(1024, 3, 1, 0.01)
+        R.step([g])
+        assert_bits_equal(R.diff(0), g, "diff_ untouched when zero_diff=0")
+    finally:
+        R.close()
+
+
+def test_boundary_conventions_like_CaffeNetTest(cos):
+    # CaffeNetTest.java:86-159 on a local net
+    desc = cos.SolverDesc([100, 10], max_iter=2000, snapshot_prefix="/tmp/cos_test_local", **HP_CIFAR)
+    net = cos.CaffeNet(desc)
+    try:
+        assert net.init(-1) is False
+        assert net.deviceID(-1) == -1
+        assert net.getInitIter(-1) == -1
+        assert net.getMaxIter(-1) == -1
+        assert net.snapshotFilename(-1, False) is None
+        assert net.connect(None) is True                      # connectnull
+        addrs = net.localAddresses()
+        assert len(addrs) == 0                                # testBasic
+        assert net.connect(addrs)
+        assert net.sync() is True
+        assert net.deviceID(0) == 0
+        assert net.init(0, True)
+        assert net.getInitIter(0) == 0
+        assert net.getMaxIter(0) == 2000
+        it = net.snapshot()
+        assert it >= 0
+        import os
+        for is_state in (True, False):
+            fn = net.snapshotFilename(it, is_state)
+            assert fn.startswith("/tmp/cos_test_local_iter_0") and os.path.exists(fn)
+            os.unlink(fn)
+        with pytest.raises(cos.CosError, match="data is NULL"):  # trainnull
+            net.train(0, None)
+        assert net.train(0, [np.zeros((2, 1, 2, 2), np.float32), np.zeros((2,), np.float32)]) is False
+        assert "gradient producer" in net.last_error()
+    finally:
+        net.deallocate()
+
+
+def test_socket_net_connectbogus(cos):
+    # CaffeNetTest.java:116-126: SocketCaffeNet.connect({"0x222","0x333"}) must fail, not hang
+    desc = cos.SolverDesc([64], **HP_CIFAR)
+    net = cos.CaffeNet(desc, "", "", 1, 2, 0, False, cos.CaffeNet.SOCKET, -1, 0)
+    try:
+        la = net.localAddresses()
+        assert len(la) == 2 and la[0] == "" and la[1].startswith("cosb200://")
+        assert net.connect(["0x222", "0x333"]) is False
+        assert net.sync_step(0) is False and "connect" in net.last_error()
+    finally:
+        net.deallocate()
+    with pytest.raises(cos.CosError, match="unable to create CaffeNet"):
+        cos.CaffeNet(desc, "", "", 1, 2, 0, False, cos.CaffeNet.NONE, -1, 0)
+
+
+def test_full_size_caffenet_properties(cos, oracle):
+    """BASELINE full size (P = 60,965,224): oracle comparison on the whole
+    buffer (the C oracle handles it in seconds) + a size-independent property:
+    with zero gradient, zero decay multipliers and zero history the weights
+    must not move (idempotence)."""
+    from caffeonspark_b200 import nets
+    desc = nets.solver_desc("caffenet")
+    assert desc.param_count == 60965224
+    sim = oracle.Simulation(1, desc.counts, desc.lr_mult, desc.decay_mult, seed=5, **desc.hyper())
+    R = Ranks(cos, desc, 1)
+    try:
+        R.set_weights([sim.data[0]])
+        R.connect()
+        for t in range(2):
+            g = sim.gradient(0, t)
+            sim.step([g])
+            R.step([g])
+        assert_bits_equal(R.weights(0), sim.data[0], "caffenet weights")
+        assert_bits_equal(R.history(0), sim.hist[0], "caffenet history")
+        ms = R.nets[0].last_kernel_ms()
+        assert 0 < ms < 50
+    finally:
+        R.close()
+    desc0 = cos.SolverDesc([60965224], [1.0], [0.0], lr_policy="fixed", base_lr=0.1, momentum=0.9, weight_decay=0.5)
+    R = Ranks(cos, desc0, 1)
+    try:
+        w0 = oracle.fill(desc0.param_count, 9, 0, 0.05)
+        R.set_weights([w0])
+        R.connect()
+        R.step([np.zeros_like(w0)])
+        assert_bits_equal(R.weights(0), w0, "idempotence under zero gradient")
+    finally:
+        R.close()

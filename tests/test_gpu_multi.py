@@ -1,0 +1,146 @@
+"""-m gpu parity of the multi-executor path through the C ABI.
+
+Runs N executors (one CaffeNet each, real connect() handshake over the peer
+adapter, real cross-GPU barrier flags and peer loads/stores) INSIDE one
+process on ONE GPU, so it runs on the single-GPU test box; the kernels of all
+ranks are co-resident (small grids).  test_gpu_multiproc.py repeats the core
+case with one process per GPU when >= 2 GPUs are visible.  Bar: bit-exact
+against the oracle (which is pinned to the reference's own socket-sync code).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from gpu_util import Ranks, assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HP = dict(lr_policy="inv", base_lr=0.01, gamma=0.0001, power=0.75, momentum=0.9, weight_decay=0.0005)
+
+
+def _run_case(cos, oracle, N, counts, lm, dm, hp, iters, seed, bf16=False, algo=0, per_rank_init=False, **opts):
+    desc = cos.SolverDesc(counts, lm, dm, grad_dtype="bf16" if bf16 else "fp32", **hp)
+    sim = oracle.Simulation(N, counts, lm, dm, seed=seed, bf16=bf16, **hp)
+    if per_rank_init:  # ranks start from DIFFERENT weights: the first on_start must reconcile them
+        for r in range(N):
+            sim.data[r] = oracle.fill(sim.P, seed + 100 + r, 0, 0.05)
+    R = Ranks(cos, desc, N, algo=algo, **opts)
+    try:
+        R.set_weights(sim.data)
+        R.connect()  # includes the first on_start(): all-gather of the owners' shards
+        start = oracle.Simulation.consistent_weights(sim)
+        for r in range(N):
+            assert_bits_equal(R.weights(r), start, f"weights after connect on rank {r}")
+        mode = R.nets[0].get_option("resolved_algo")
+        for t in range(iters):
+            grads = [oracle.fill(sim.P, seed, (t + 1) * 4096 + r, 0.01) for r in range(N)]
+            sim.step()
+            R.step(grads)
+            cw, ch = sim.consistent_weights(), sim.consistent_history()
+            for r in range(N):
+                assert_bits_equal(R.weights(r), cw, f"N={N} weights iter {t} rank {r}")
+                o, s = cos.chunk(sim.P, N, r)
+                if mode == 2:  # one-shot keeps the full history everywhere
+                    assert_bits_equal(R.history(r), ch, f"N={N} full history iter {t} rank {r}")
+                else:          # two-shot: history is valid on the owner only (as in the reference)
+                    assert_bits_equal(R.history(r)[o:o + s], ch[o:o + s], f"N={N} own history iter {t} rank {r}")
+                assert R.nets[r].shard() == (o, s)
+                assert R.nets[r].iter() == sim.iter
+                assert not R.diff(r).any()
+        return R, sim
+    except Exception:
+        R.close()
+        raise
+
+
+def _cases():
+    with open(os.path.join(GOLD, "ref_sync_cases.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(_cases().keys()))
+@pytest.mark.parametrize("algo", [1, 2])
+def test_matches_reference_golden_vectors(cos, oracle, name, algo):
+    """Directly against vectors produced by the reference's own code."""
+    m = _cases()[name]
+    gold = np.load(os.path.join(GOLD, "ref_sync_cases.npz"))
+    R, sim = _run_case(cos, oracle, m["N"], m["counts"], m["lr_mult"], m["decay_mult"], m["hyper"], m["iters"],
+                       m["seed"], bf16=m["bf16"], algo=algo)
+    try:
+        for r in range(m["N"]):
+            assert_bits_equal(R.weights(r), gold[f"{name}/final"], f"{name} final weights rank {r}")
+            o, s = cos.chunk(sim.P, m["N"], r)
+            assert_bits_equal(R.history(r)[o:o + s], gold[f"{name}/h/{m['iters'] - 1}/{r}"], f"{name} history {r}")
+    finally:
+        R.close()
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("algo", [1, 2])
+def test_lenet_layout_world_sizes(cos, oracle, N, algo):
+    counts = [500, 20, 25000, 50, 40000, 500, 5000, 10]  # LeNet blob structure, ip1 shrunk to keep it quick
+    R, _ = _run_case(cos, oracle, N, counts, [1, 2] * 4, [1, 1] * 4, HP, 3, 31, algo=algo)
+    R.close()
+
+
+@pytest.mark.parametrize("N,algo", [(2, 1), (4, 1), (8, 1), (4, 2)])
+def test_bf16_wire(cos, oracle, N, algo):
+    counts = [2400, 32, 25600, 32, 5120, 64, 6553, 64, 640, 10]
+    hp = dict(lr_policy="fixed", base_lr=0.001, momentum=0.9, weight_decay=0.004)
+    R, _ = _run_case(cos, oracle, N, counts, [1, 2] * 5, [1, 1] * 5, hp, 3, 41, bf16=True, algo=algo)
+    R.close()
+
+
+def test_first_on_start_reconciles_different_initial_weights(cos, oracle):
+    R, _ = _run_case(cos, oracle, 4, [1001, 13], [1, 2], [1, 0], HP, 2, 51, per_rank_init=True, algo=1)
+    R.close()
+
+
+def test_generic_world_size_and_odd_shapes(cos, oracle):
+    # N=6,7 (templated) and tiny P < N (empty shards), P == N
+    for N, counts in [(6, [997, 3]), (7, [64, 1]), (8, [3]), (4, [4]), (3, [1])]:
+        for algo in (1, 2):
+            R, _ = _run_case(cos, oracle, N, counts, None, None, HP, 2, 61, algo=algo)
+            R.close()
+
+
+def test_auto_algo_switch_is_size_based(cos):
+    small = cos.SolverDesc([1000], **HP)
+    big = cos.SolverDesc([1 << 20], **HP)
+    for desc, want in ((small, 2), (big, 1)):
+        net = cos.CaffeNet(desc, "", "", 1, 2, 0, True, cos.CaffeNet.SOCKET, -1, 0)
+        assert net.get_option("resolved_algo") == want
+        net.deallocate()
+
+
+def test_missing_peer_times_out_instead_of_hanging(cos, oracle):
+    """A dead peer must surface as an error (the reference blocks forever in
+    BlockingQueue::pop)."""
+    desc = cos.SolverDesc([4096], **HP)
+    R = Ranks(cos, desc, 2, timeout_ms=300)
+    try:
+        R.connect()
+        assert R.nets[0].sync_step(0)          # rank 1 never launches
+        assert R.nets[0].synchronize() is False
+        assert "timed out" in R.nets[0].last_error()
+    finally:
+        R.close()
+
+
+def test_snapshot_gathers_sharded_history(cos, oracle, tmp_path):
+    counts = [3000, 100]
+    hp = dict(HP, snapshot_prefix=str(tmp_path / "snap"))
+    R, sim = _run_case(cos, oracle, 4, counts, [1, 2], [1, 0], hp, 2, 71, algo=1)
+    try:
+        it = R.nets[0].snapshot()              # rank 0 only, as CaffeProcessor does
+        assert it == 2
+        raw = np.fromfile(R.nets[0].snapshotFilename(it, True), dtype=np.uint8)
+        hist = raw[-4 * sim.P:].view(np.float32)
+        assert_bits_equal(hist, sim.consistent_history(), "snapshot history = owners' shards")
+        rawm = np.fromfile(R.nets[0].snapshotFilename(it, False), dtype=np.uint8)
+        assert_bits_equal(rawm[-4 * sim.P:].view(np.float32), sim.consistent_weights(), "snapshot weights")
+    finally:
+        R.close()

@@ -1,0 +1,86 @@
+"""-m gpu: the reference-facing call, CaffeNet.train(solver_index, FloatBlob[])
+(CaffeNet.java:120, CaffeNetTest.testTrain :270-321): host blobs in, one
+Solver::Step, with the PyTorch gradient producer standing in for
+Net::ForwardBackward.  Checks the step against the oracle given the SAME
+gradient, and that training actually reduces the loss."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import assert_bits_equal, to_host
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_lenet_from_prototxt(cos, oracle, tmp_path):
+    from caffeonspark_b200 import harness, nets
+    solver = nets.write_prototxts("lenet", str(tmp_path))
+    net = cos.CaffeNet(solver, "", "", 1, 1, 0, True, cos.CaffeNet.NONE, -1, 0)  # allocate(prototxt...) path
+    try:
+        assert net.param_count() == nets.EXPECTED_PARAM_COUNT["lenet"]
+        assert net.connect(net.localAddresses())
+        assert net.init(0, True)
+        net.set_option("zero_diff", 0)  # keep the gradient so the test can feed it to the oracle
+        prod = harness.make_producer("lenet", net)
+        desc = net.desc
+        rng = np.random.RandomState(0)
+        x = torch.from_numpy(rng.rand(64, 1, 28, 28).astype(np.float32)).pin_memory()
+        y = torch.from_numpy(rng.randint(0, 10, (64, 1, 1, 1)).astype(np.float32)).pin_memory()
+        losses = []
+        for t in range(20):
+            w_before, h_before = to_host(net.data()), to_host(net.history())
+            net.diff().zero_()
+            torch.cuda.synchronize()
+            rate = net.learning_rate()
+            assert net.train(0, [x, y]), net.last_error()
+            losses.append(net.last_loss())
+            g = to_host(net.diff())  # the gradient the producer accumulated (diff_ not cleared)
+            oracle.apply_update(0, desc.param_count, w_before, g.copy(), h_before, desc.counts, desc.lr_mult,
+                                desc.decay_mult, np.float32(rate), np.float32(desc.momentum),
+                                np.float32(desc.weight_decay))
+            assert_bits_equal(to_host(net.data()), w_before, f"weights after train() iter {t}")
+            assert_bits_equal(to_host(net.history()), h_before, f"history after train() iter {t}")
+        assert net.iter() == 20
+        assert np.isfinite(losses).all() and losses[-1] < losses[0] and losses[-1] < 50.0  # CaffeNetTest: loss < 50
+        assert prod is not None
+    finally:
+        net.deallocate()
+
+
+def test_train_two_ranks_in_process(cos, oracle):
+    """Two executors, real train() calls from two threads (CaffeProcessor runs
+    one solver thread per device), gradients from the PyTorch producer."""
+    import concurrent.futures as cf
+    from caffeonspark_b200 import harness, nets
+    desc = nets.solver_desc("cifar10_quick")
+    netz = [cos.CaffeNet(desc, "", "", 1, 2, r, True, cos.CaffeNet.SOCKET, -1, 0) for r in range(2)]
+    try:
+        for n in netz:
+            n.set_option("grid", 8)
+            n.set_option("block", 128)
+            n.set_option("barrier_timeout_ms", 20000)
+        prods = [harness.make_producer("cifar10_quick", n, seed=5) for n in netz]  # same init on both ranks
+        table = [n.localAddresses() for n in netz]
+        with cf.ThreadPoolExecutor(2) as ex:
+            assert all(ex.map(lambda r: netz[r].connect([table[p][r] if p != r else "" for p in range(2)]), range(2)))
+        rng = np.random.RandomState(1)
+        batches = [(torch.from_numpy(rng.rand(100, 3, 32, 32).astype(np.float32)),
+                    torch.from_numpy(rng.randint(0, 10, (100,)).astype(np.float32))) for _ in range(2)]
+
+        def run(r):
+            out = []
+            for _ in range(6):
+                assert netz[r].train(0, list(batches[r])), netz[r].last_error()
+                out.append(netz[r].last_loss())
+            return out
+
+        with cf.ThreadPoolExecutor(2) as ex:
+            losses = list(ex.map(run, range(2)))
+        w0, w1 = to_host(netz[0].data()), to_host(netz[1].data())
+        assert_bits_equal(w0, w1, "ranks hold identical weights after synchronous SGD")
+        assert all(np.isfinite(l).all() for l in losses)
+        assert losses[0][-1] < losses[0][0]
+        assert prods
+    finally:
+        with cf.ThreadPoolExecutor(2) as ex:
+            list(ex.map(lambda n: n.deallocate(), netz))
