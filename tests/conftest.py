@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# The in-process multi-rank tests run one spinning kernel per rank on ONE GPU.  Streams that share a
+# hardware work queue serialise (a kernel queued behind a spinning one never starts), so ask for the
+# maximum number of queues BEFORE the CUDA context exists.  Irrelevant in deployment (one rank per GPU).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
