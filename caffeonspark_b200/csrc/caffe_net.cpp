@@ -89,6 +89,7 @@ CaffeNet::~CaffeNet() {
     if (status_) cudaFreeHost(status_);
     if (ev_start_) cudaEventDestroy(ev_start_);
     if (ev_stop_) cudaEventDestroy(ev_stop_);
+    if (ev_done_) cudaEventDestroy(ev_done_);
     if (stream_) cudaStreamDestroy(stream_);
     arena_.destroy();
     cudaGetLastError();
@@ -189,6 +190,7 @@ bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::str
   COS_RT(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   COS_RT(cudaEventCreate(&ev_start_));
   COS_RT(cudaEventCreate(&ev_stop_));
+  COS_RT(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
   return true;
 }
 
@@ -268,6 +270,8 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
     COS_RT(cudaEventRecord(ev_stop_, stream));
     ev_valid_ = true;
   }
+  COS_RT(cudaEventRecord(ev_done_, stream));  // what synchronize() waits on (works for caller-owned streams)
+  done_valid_ = true;
   ++launches_;
   return true;
 }
@@ -311,10 +315,14 @@ bool CaffeNet::check_status(std::string* err) {
   return false;
 }
 
+// Waits for the last launch (on whatever stream it went to) and the net's own
+// stream.  Deliberately NOT cudaDeviceSynchronize: with several executors in
+// one process a device-wide wait from one thread can stall another thread's
+// launch while the first one's kernel is spinning on it.
 bool CaffeNet::synchronize(std::string* err) {
   COS_RT(cudaSetDevice(device_));
+  if (done_valid_) COS_RT(cudaEventSynchronize(ev_done_));
   COS_RT(cudaStreamSynchronize(stream_));
-  COS_RT(cudaDeviceSynchronize());
   return check_status(err);
 }
 
@@ -446,8 +454,8 @@ bool write_flat(const std::string& path, const char* magic, int iter, int curren
 
 int CaffeNet::snapshot(std::string* err) {
   std::lock_guard<std::mutex> g(mu_);
-  if (cudaSetDevice(device_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess ||
-      cudaDeviceSynchronize() != cudaSuccess) {
+  if (cudaSetDevice(device_) != cudaSuccess || (done_valid_ && cudaEventSynchronize(ev_done_) != cudaSuccess) ||
+      cudaStreamSynchronize(stream_) != cudaSuccess) {
     *err = rt_err("snapshot: device sync", cudaGetLastError());
     return -1;
   }

@@ -111,8 +111,8 @@ class CaffeNet {
   bool connected_ = false;
 
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t ev_start_ = nullptr, ev_stop_ = nullptr;
-  bool ev_valid_ = false;
+  cudaEvent_t ev_start_ = nullptr, ev_stop_ = nullptr, ev_done_ = nullptr;
+  bool ev_valid_ = false, done_valid_ = false;
   int iter_ = 0;
   int current_step_ = 0;  // SGDSolver::current_step_
   uint32_t epoch_ = 0;

@@ -23,6 +23,7 @@ HP = dict(lr_policy="inv", base_lr=0.01, gamma=0.0001, power=0.75, momentum=0.9,
 
 def _run_case(cos, oracle, N, counts, lm, dm, hp, iters, seed, bf16=False, algo=0, per_rank_init=False, **opts):
     desc = cos.SolverDesc(counts, lm, dm, grad_dtype="bf16" if bf16 else "fp32", **hp)
+    hp = {k: v for k, v in hp.items() if k != "snapshot_prefix"}
     sim = oracle.Simulation(N, counts, lm, dm, seed=seed, bf16=bf16, **hp)
     if per_rank_init:  # ranks start from DIFFERENT weights: the first on_start must reconcile them
         for r in range(N):
