@@ -150,6 +150,7 @@ def run_ours(args):
     net = cl.net
     if args.algo:
         net.set_option("algo", args.algo)
+    net.set_option("kernel", args.kernel)
     net.set_option("barrier_timeout_ms", 60000)
     prod = harness.make_producer(name, net)
     cl.start()
@@ -285,6 +286,7 @@ def run_ours(args):
                                f"PyTorch forward/backward + fused sync kernel",
                    "global_batch": world * batch, "parallelism": f"dp{world}",
                    "algo": {0: "local", 1: "two_shot", 2: "one_shot"}[mode], "grad_dtype": args.grad_dtype,
+                   "kernel": {0: "ldg_stg_vector", 1: "tma_bulk_pipeline"}[args.kernel],
                    "producer": "cuda_graph" if graph is not None else "eager",
                    "l2": "flushed between steps (256 MiB write outside the timed events)" if need_flush
                          else f"working set {working_set >> 20} MiB > 126 MiB L2"},
@@ -295,7 +297,8 @@ def run_ours(args):
                 "last_loss": last_loss},
         "gpu_launches": int(launches), "e2e_gpu_launches": int(e2e_launches),
         "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fused_sync_sgd_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": "fused_sync_sgd_tma_kernel" if args.kernel else
+                     "fused_sync_sgd_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes": alg, "peak_source": (peak_kind + " MEASURED_PEAKS.json hbm_gbs") if
                      world == 1 else "B200_PROFILING.md measured peer copy per direction"},
         "split_ms": {"forward_backward": fb_ms, "fused_sync_kernel": k_ms},
@@ -321,7 +324,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(name, desc, batch, 1, fb_ms)
     if rank == 0 and args.kernels:
-        out["kernel_rooflines"] = kernel_rooflines(C, nets, peaks, world)
+        out["kernel_rooflines"] = kernel_rooflines(C, nets, peaks, world, args.kernel)
     net.deallocate()
     if world > 1:
         dist.barrier()
@@ -330,7 +333,7 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def kernel_rooflines(C, nets, peaks, world):
+def kernel_rooflines(C, nets, peaks, world, kernel=0):
     """Fused-kernel-only timing of the three BASELINE layouts at N=1 (HBM roofline)."""
     import torch
     res = {}
@@ -341,6 +344,7 @@ def kernel_rooflines(C, nets, peaks, world):
         desc = nets.solver_desc(name)
         net = C.CaffeNet(desc, "", "", 1, 1, 0, True, 0, torch.cuda.current_device() - 1, 0)
         net.connect([])
+        net.set_option("kernel", kernel)
         P = net.param_count()
         net.diff().normal_(0, 0.01)
         ms = []
@@ -451,10 +455,13 @@ def run_sweep(args):
     sizes = [64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20, 512 << 20]
     for S in sizes:
         P = S // 4
-        for algo in ((1, 2) if (world > 1 and S <= (4 << 20)) else (1,)):
+        variants = [(a, k) for a in ((1, 2) if (world > 1 and S <= (4 << 20)) else (1,)) for k in (0, 1)]
+        nccl_ms = None
+        for algo, kern in variants:
             desc = C.SolverDesc([P], lr_policy="fixed", base_lr=0.01, momentum=0.9, weight_decay=0.0005)
             cl = harness.Cluster(desc, rank=rank, world=world, device=local)
             net = cl.net
+            net.set_option("kernel", kern)
             if world > 1:
                 net.set_option("algo", algo)
             net.set_option("barrier_timeout_ms", 60000)
@@ -476,12 +483,13 @@ def run_sweep(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 k = float(t.item())
             row = {"bytes": S, "algo": {1: "two_shot", 2: "one_shot"}[algo] if world > 1 else "local",
-                   "kernel_ms": k, "min_ms": min(ms)}
+                   "kernel": "tma" if kern else "ldg", "kernel_ms": k, "min_ms": min(ms)}
             if world > 1:
                 row["bus_gbs"] = S * 2 * (world - 1) / world / (k * 1e-3) / 1e9
+            if world > 1 and nccl_ms is None:
                 # NCCL all-reduce of the same message (the library baseline the fused kernel must beat);
                 # it does NOT include the SGD update
-                buf = torch.empty(P, device="cuda")
+                buf = torch.zeros(P, device="cuda")
                 evs = []
                 for i in range(args.warmup + args.steps):
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -492,7 +500,10 @@ def run_sweep(args):
                     torch.cuda.synchronize()
                     if i >= args.warmup:
                         evs.append(a.elapsed_time(b))
-                row["nccl_allreduce_ms"] = sorted(evs)[len(evs) // 2]
+                nccl_ms = sorted(evs)[len(evs) // 2]
+                del buf
+            if world > 1:
+                row["nccl_allreduce_ms"] = nccl_ms
             else:
                 row["hbm_gbs"] = 24 * P / (k * 1e-3) / 1e9
             rows.append(row)
@@ -514,6 +525,7 @@ def main():
     ap.add_argument("--workload", default="lenet", choices=["lenet", "cifar10_quick", "caffenet"])
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 two-shot, 2 one-shot")
+    ap.add_argument("--kernel", type=int, default=0, help="0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", action="store_true", default=True)

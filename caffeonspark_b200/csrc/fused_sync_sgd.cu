@@ -31,185 +31,13 @@
 // shard owner reads or writes, and per-CTA (not grid-wide) cross-GPU barriers
 // are sufficient for all three phases.
 #include "fused_sync_sgd.hpp"
-
-#include <cuda_bf16.h>
-#include <stdint.h>
+#include "sync_device.cuh"
 
 namespace cosb {
 namespace {
 
 constexpr int kDefaultThreads = 512;
 constexpr int kMaxSegSmem = 1024;
-
-// ------------------------------------------------------------ PTX helpers
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// streaming 128-bit load that does not allocate in L1 (each element is read once)
-__device__ __forceinline__ float4 ld_stream(const float* p) {
-  float4 v;
-  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ uint2 ld_stream_u2(const uint16_t* p) {
-  uint2 v;
-  asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ void st_vec(float* p, const float4& v) {
-  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
-}
-
-__device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
-
-__device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
-  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
-}
-
-// ------------------------------------------------------ cross-GPU barrier
-
-__device__ __forceinline__ uint32_t* flag_slot(uint32_t* base, int which, int cta, int src) {
-  return base + (static_cast<size_t>(which) * kMaxCtas + cta) * kMaxRanks + src;
-}
-
-// Barrier between CTA blockIdx.x of every rank.  Thread t < world handles peer
-// t: it publishes this launch's epoch into the peer's flag slot [cta][rank]
-// and spins on the local slot [cta][t].  Flags are only ever polled in LOCAL
-// memory (peers store into it), so spinning costs no NVLink bandwidth.
-// The leading __syncthreads + system fence make every store of the CTA (e.g.
-// weight pushes into peer memory) visible before the flag is.
-// Returns false if a peer did not arrive within timeout_ns (status is set).
-__device__ bool cta_barrier(const SyncParams& p, int which, int* s_abort) {
-  __syncthreads();
-  const int t = threadIdx.x;
-  if (t < p.world && t != p.rank) {
-    __threadfence_system();
-    st_release_sys(flag_slot(p.flags[t], which, blockIdx.x, p.rank), p.epoch);
-    const uint32_t* mine = flag_slot(p.flags[p.rank], which, blockIdx.x, t);
-    const unsigned long long t0 = globaltimer_ns();
-    unsigned spins = 0;
-    for (;;) {
-      uint32_t v = ld_acquire_sys(mine);
-      if (static_cast<int32_t>(v - p.epoch) >= 0) break;
-      if ((++spins & 0x3ffu) == 0) {
-        if (*reinterpret_cast<volatile int*>(s_abort)) break;
-        if (globaltimer_ns() - t0 > p.timeout_ns) {
-          atomicExch(p.status, 100 + which * 32 + t);  // which barrier, which peer
-          *reinterpret_cast<volatile int*>(s_abort) = 1;
-          break;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  return *reinterpret_cast<volatile int*>(s_abort) == 0;
-}
-
-// ------------------------------------------------------------- partition
-
-struct ShardRange {
-  uint64_t lo, hi;        // element range
-  uint64_t vec_lo;        // first float4 index fully inside
-  uint64_t nvec;          // number of float4 vectors fully inside
-  uint64_t head_end;      // [lo, head_end) scalar head
-  uint64_t tail_begin;    // [tail_begin, hi) scalar tail
-};
-
-// socket_sync_cpu.cpp:46-54 chunk(): multiply first, then divide, in 64 bit.
-__device__ __forceinline__ ShardRange shard_range(uint64_t count, int world, int s) {
-  ShardRange r;
-  r.lo = static_cast<uint64_t>(s) * count / static_cast<uint64_t>(world);
-  r.hi = (static_cast<uint64_t>(s) + 1) * count / static_cast<uint64_t>(world);
-  uint64_t vlo = (r.lo + 3) >> 2, vhi = r.hi >> 2;
-  if (vhi > vlo) {
-    r.vec_lo = vlo;
-    r.nvec = vhi - vlo;
-    r.head_end = vlo << 2;
-    r.tail_begin = vhi << 2;
-  } else {
-    r.vec_lo = vlo;
-    r.nvec = 0;
-    r.head_end = r.hi;  // everything scalar
-    r.tail_begin = r.hi;
-  }
-  return r;
-}
-
-// ----------------------------------------------------------- SGD element
-
-struct SegCursor {
-  const uint64_t* end;
-  const float* lr_mult;
-  const float* decay_mult;
-  int nseg;
-  int k;
-  __device__ __forceinline__ void seek(uint64_t i) {  // binary search: first k with end[k] > i
-    int lo = 0, hi = nseg - 1;
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (end[mid] > i) hi = mid; else lo = mid + 1;
-    }
-    k = lo;
-  }
-  __device__ __forceinline__ void advance(uint64_t i) {
-    while (k < nseg - 1 && i >= end[k]) ++k;
-  }
-};
-
-// Regularize (L2) + ComputeUpdateValue + Blob::Update for one element, in the
-// reference's operation order with one rounding per operation:
-//   g = ld*w + g ; h = m*h ; h = lr*g + h ; w = (-1*h) + w
-__device__ __forceinline__ void sgd_element(float g, float& w, float& h, float lr, float ld, float m) {
-  if (ld != 0.f) g = __fadd_rn(__fmul_rn(ld, w), g);
-  h = __fmul_rn(m, h);
-  h = __fadd_rn(__fmul_rn(lr, g), h);
-  w = __fadd_rn(__fmul_rn(-1.0f, h), w);
-}
-
-__device__ __forceinline__ void sgd_vec(const SyncParams& p, SegCursor& c, uint64_t i, const float4& g, float4& w,
-                                        float4& h) {
-  c.advance(i);
-  if (i + 3 < c.end[c.k]) {
-    const float lr = __fmul_rn(p.rate, c.lr_mult[c.k]);
-    const float ld = __fmul_rn(p.weight_decay, c.decay_mult[c.k]);
-    sgd_element(g.x, w.x, h.x, lr, ld, p.momentum);
-    sgd_element(g.y, w.y, h.y, lr, ld, p.momentum);
-    sgd_element(g.z, w.z, h.z, lr, ld, p.momentum);
-    sgd_element(g.w, w.w, h.w, lr, ld, p.momentum);
-  } else {  // the vector straddles one or more blob boundaries
-    const float gg[4] = {g.x, g.y, g.z, g.w};
-    float ww[4] = {w.x, w.y, w.z, w.w};
-    float hh[4] = {h.x, h.y, h.z, h.w};
-    int k = c.k;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      while (k < c.nseg - 1 && i + e >= c.end[k]) ++k;
-      sgd_element(gg[e], ww[e], hh[e], __fmul_rn(p.rate, c.lr_mult[k]), __fmul_rn(p.weight_decay, c.decay_mult[k]),
-                  p.momentum);
-    }
-    w = make_float4(ww[0], ww[1], ww[2], ww[3]);
-    h = make_float4(hh[0], hh[1], hh[2], hh[3]);
-  }
-}
 
 // --------------------------------------------------------- reduce (phase 1)
 

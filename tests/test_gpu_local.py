@@ -25,11 +25,12 @@ LAYOUTS = {
 
 @pytest.mark.parametrize("name", sorted(LAYOUTS))
 @pytest.mark.parametrize("bf16", [False, True])
-def test_local_update_bit_exact(cos, oracle, name, bf16):
+@pytest.mark.parametrize("kernel", [0, 1], ids=["ldg", "tma"])
+def test_local_update_bit_exact(cos, oracle, name, bf16, kernel):
     counts, lm, dm, hp = LAYOUTS[name]
     desc = cos.SolverDesc(counts, lm, dm, grad_dtype="bf16" if bf16 else "fp32", **hp)
     sim = oracle.Simulation(1, counts, lm, dm, seed=7, bf16=bf16, **hp)
-    R = Ranks(cos, desc, 1)
+    R = Ranks(cos, desc, 1, kernel=kernel)
     try:
         R.set_weights([sim.data[0]])
         R.connect()
@@ -110,7 +111,8 @@ def test_socket_net_connectbogus(cos):
         cos.CaffeNet(desc, "", "", 1, 2, 0, False, cos.CaffeNet.NONE, -1, 0)
 
 
-def test_full_size_caffenet_properties(cos, oracle):
+@pytest.mark.parametrize("kernel", [0, 1], ids=["ldg", "tma"])
+def test_full_size_caffenet_properties(cos, oracle, kernel):
     """BASELINE full size (P = 60,965,224): oracle comparison on the whole
     buffer (the C oracle handles it in seconds) + a size-independent property:
     with zero gradient, zero decay multipliers and zero history the weights
@@ -119,7 +121,7 @@ def test_full_size_caffenet_properties(cos, oracle):
     desc = nets.solver_desc("caffenet")
     assert desc.param_count == 60965224
     sim = oracle.Simulation(1, desc.counts, desc.lr_mult, desc.decay_mult, seed=5, **desc.hyper())
-    R = Ranks(cos, desc, 1)
+    R = Ranks(cos, desc, 1, kernel=kernel)
     try:
         R.set_weights([sim.data[0]])
         R.connect()
@@ -134,7 +136,7 @@ def test_full_size_caffenet_properties(cos, oracle):
     finally:
         R.close()
     desc0 = cos.SolverDesc([60965224], [1.0], [0.0], lr_policy="fixed", base_lr=0.1, momentum=0.9, weight_decay=0.5)
-    R = Ranks(cos, desc0, 1)
+    R = Ranks(cos, desc0, 1, kernel=kernel)
     try:
         w0 = oracle.fill(desc0.param_count, 9, 0, 0.05)
         R.set_weights([w0])

@@ -62,14 +62,20 @@ def _cases():
         return json.load(f)
 
 
-@pytest.mark.parametrize("name", sorted(_cases().keys()))
+# More than 4 spinning kernels of one process are not reliably co-scheduled on one GPU (observed on the
+# B200 box); world sizes 5..8 are covered with one PROCESS per rank in test_gpu_multiproc.py.
+MAX_INPROC = 4
+
+
+@pytest.mark.parametrize("name", sorted(k for k, m in _cases().items() if m["N"] <= MAX_INPROC))
 @pytest.mark.parametrize("algo", [1, 2])
-def test_matches_reference_golden_vectors(cos, oracle, name, algo):
+@pytest.mark.parametrize("kernel", [0, 1], ids=["ldg", "tma"])
+def test_matches_reference_golden_vectors(cos, oracle, name, algo, kernel):
     """Directly against vectors produced by the reference's own code."""
     m = _cases()[name]
     gold = np.load(os.path.join(GOLD, "ref_sync_cases.npz"))
     R, sim = _run_case(cos, oracle, m["N"], m["counts"], m["lr_mult"], m["decay_mult"], m["hyper"], m["iters"],
-                       m["seed"], bf16=m["bf16"], algo=algo)
+                       m["seed"], bf16=m["bf16"], algo=algo, kernel=kernel)
     try:
         for r in range(m["N"]):
             assert_bits_equal(R.weights(r), gold[f"{name}/final"], f"{name} final weights rank {r}")
@@ -79,19 +85,21 @@ def test_matches_reference_golden_vectors(cos, oracle, name, algo):
         R.close()
 
 
-@pytest.mark.parametrize("N", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("N", [2, 3, 4])
 @pytest.mark.parametrize("algo", [1, 2])
-def test_lenet_layout_world_sizes(cos, oracle, N, algo):
+@pytest.mark.parametrize("kernel", [0, 1], ids=["ldg", "tma"])
+def test_lenet_layout_world_sizes(cos, oracle, N, algo, kernel):
     counts = [500, 20, 25000, 50, 40000, 500, 5000, 10]  # LeNet blob structure, ip1 shrunk to keep it quick
-    R, _ = _run_case(cos, oracle, N, counts, [1, 2] * 4, [1, 1] * 4, HP, 3, 31, algo=algo)
+    R, _ = _run_case(cos, oracle, N, counts, [1, 2] * 4, [1, 1] * 4, HP, 3, 31, algo=algo, kernel=kernel)
     R.close()
 
 
-@pytest.mark.parametrize("N,algo", [(2, 1), (4, 1), (8, 1), (4, 2)])
-def test_bf16_wire(cos, oracle, N, algo):
+@pytest.mark.parametrize("N,algo", [(2, 1), (3, 1), (4, 1), (4, 2)])
+@pytest.mark.parametrize("kernel", [0, 1], ids=["ldg", "tma"])
+def test_bf16_wire(cos, oracle, N, algo, kernel):
     counts = [2400, 32, 25600, 32, 5120, 64, 6553, 64, 640, 10]
     hp = dict(lr_policy="fixed", base_lr=0.001, momentum=0.9, weight_decay=0.004)
-    R, _ = _run_case(cos, oracle, N, counts, [1, 2] * 5, [1, 1] * 5, hp, 3, 41, bf16=True, algo=algo)
+    R, _ = _run_case(cos, oracle, N, counts, [1, 2] * 5, [1, 1] * 5, hp, 3, 41, bf16=True, algo=algo, kernel=kernel)
     R.close()
 
 
@@ -101,11 +109,12 @@ def test_first_on_start_reconciles_different_initial_weights(cos, oracle):
 
 
 def test_generic_world_size_and_odd_shapes(cos, oracle):
-    # N=6,7 (templated) and tiny P < N (empty shards), P == N
-    for N, counts in [(6, [997, 3]), (7, [64, 1]), (8, [3]), (4, [4]), (3, [1])]:
+    # odd sizes, tiny P < N (empty shards), P == N, both kernels
+    for N, counts in [(3, [997, 3]), (4, [64, 1]), (4, [3]), (4, [4]), (3, [1]), (2, [9, 8, 7])]:
         for algo in (1, 2):
-            R, _ = _run_case(cos, oracle, N, counts, None, None, HP, 2, 61, algo=algo)
-            R.close()
+            for kernel in (0, 1):
+                R, _ = _run_case(cos, oracle, N, counts, None, None, HP, 2, 61, algo=algo, kernel=kernel)
+                R.close()
 
 
 def test_auto_algo_switch_is_size_based(cos):

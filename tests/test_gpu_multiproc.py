@@ -23,33 +23,42 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, algo, bf16, q):
+def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dev = 0 if shared_gpu else rank
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
+                      LOCAL_RANK=str(dev))
     import torch
     import torch.distributed as dist
     import caffeonspark_b200 as C
     from caffeonspark_b200.harness import Cluster
     from oracle import oracle as O
     from gpu_util import to_dev, to_host
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    torch.cuda.set_device(dev)
+    if shared_gpu:  # NCCL refuses two ranks on one GPU; the address exchange only needs a host backend
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{dev}"))
     try:
-        counts, lm, dm = [500, 20, 25000, 50, 400000, 500, 5000, 10], [1, 2] * 4, [1, 1] * 4
+        counts, lm, dm = ([500, 20, 25000, 50, 400000, 500, 5000, 10] if not shared_gpu else
+                          [500, 20, 2500, 50, 4000, 500, 5000, 10]), [1, 2] * 4, [1, 1] * 4
         hp = dict(lr_policy="inv", base_lr=0.01, gamma=0.0001, power=0.75, momentum=0.9, weight_decay=0.0005)
         desc = C.SolverDesc(counts, lm, dm, grad_dtype="bf16" if bf16 else "fp32", **hp)
         sim = O.Simulation(world, counts, lm, dm, seed=77, bf16=bf16, **hp)
-        cl = Cluster(desc, rank=rank, world=world, device=rank)
+        cl = Cluster(desc, rank=rank, world=world, device=dev)
         net = cl.net
         net.set_option("algo", algo)
-        net.set_option("barrier_timeout_ms", 15000)
+        net.set_option("kernel", kernel)
+        net.set_option("barrier_timeout_ms", 60000 if shared_gpu else 15000)
+        if shared_gpu:  # contexts time-slice on the one GPU: keep the spinning grids tiny
+            net.set_option("grid", 2)
+            net.set_option("block", 128)
         to_dev(net.data(), sim.data[rank])
         torch.cuda.synchronize()
         cl.start()
         ok = True
-        for t in range(3):
+        for t in range(2 if shared_gpu else 3):
             g = O.fill(sim.P, 77, (t + 1) * 4096 + rank, 0.01)
             sim.step()
             to_dev(net.diff(), g)
@@ -68,16 +77,39 @@ def _worker(rank, world, port, algo, bf16, q):
 
 
 @pytest.mark.skipif(gpu_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("algo,bf16", [(1, False), (2, False), (1, True)])
-def test_one_process_per_gpu_bit_exact(cos, oracle, algo, bf16):
+@pytest.mark.parametrize("algo,bf16,kernel", [(1, False, 0), (2, False, 0), (1, True, 0), (1, False, 1), (2, False, 1),
+                                              (1, True, 1)])
+def test_one_process_per_gpu_bit_exact(cos, oracle, algo, bf16, kernel):
     import torch.multiprocessing as mp
     world = min(gpu_count(), 8)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, algo, bf16, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, algo, bf16, q, False, kernel)) for r in range(world)]
     [p.start() for p in procs]
     [p.join(300) for p in procs]
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert all(ok for _, ok, _, _ in res), res
+
+
+@pytest.mark.skipif(gpu_count() < 1, reason="needs a GPU")
+@pytest.mark.parametrize("world,algo,bf16,kernel", [(2, 1, False, 0), (3, 2, False, 1), (5, 1, True, 0),
+                                                    (8, 1, False, 1), (8, 2, False, 0)])
+def test_processes_sharing_one_gpu_bit_exact(cos, oracle, world, algo, bf16, kernel):
+    """Several executor PROCESSES on the single test GPU: the cross-process
+    descriptor-passing / VMM import path and the device-side barriers between
+    different CUDA contexts (time-sliced, so slow but must be exact)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, algo, bf16, q, True, kernel)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(420) for p in procs]
     for p in procs:
         if p.is_alive():
             p.kill()
