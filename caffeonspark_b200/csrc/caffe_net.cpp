@@ -404,6 +404,7 @@ bool CaffeNet::set_option(const std::string& name, int64_t v, std::string* err) 
   else if (name == "barrier_timeout_ms") opt_timeout_ms_ = v;
   else if (name == "one_shot_max_bytes") opt_one_shot_max_bytes_ = v;
   else if (name == "iter") { iter_ = static_cast<int>(v); }
+  else if (name == "initial_gather") opt_initial_gather_ = v != 0;
   else {
     *err = "unknown option '" + name + "'";
     return false;
@@ -422,6 +423,7 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "nvls") return opt_nvls_;
   if (name == "barrier_timeout_ms") return opt_timeout_ms_;
   if (name == "one_shot_max_bytes") return opt_one_shot_max_bytes_;
+  if (name == "initial_gather") return opt_initial_gather_;
   if (name == "transport") return arena_.transport();
   if (name == "default_grid") return default_sync_grid(device_);
   return -1;
@@ -613,9 +615,14 @@ bool NvlinkCaffeNet::connect(const std::vector<std::string>& addresses, std::str
   // owners' weight shards (socket_sync_cpu.cpp:102-105), so that all ranks
   // start from the same weights even if they were initialised differently.
   if (!adapter_->barrier(timeout, err)) return false;
-  if (!all_gather_weights(nullptr, true, err)) return false;
-  if (!synchronize(err)) return false;
-  if (!adapter_->barrier(timeout, err)) return false;
+  if (opt_initial_gather_) {
+    if (!all_gather_weights(nullptr, true, err)) return false;
+    // every rank has LAUNCHED before any rank blocks on the device (matters when several executors
+    // live in one process: a thread waiting on the GPU must not be able to delay a peer's launch)
+    if (!adapter_->barrier(timeout, err)) return false;
+    if (!synchronize(err)) return false;
+    if (!adapter_->barrier(timeout, err)) return false;
+  }
   return true;
 }
 

@@ -126,6 +126,7 @@ class CaffeNet {
   int opt_kernel_ = 0;
   int opt_timing_ = 1;
   int opt_nvls_ = 0;
+  int opt_initial_gather_ = 1;  // connect() runs the first on_start() (all-gather of weight shards)
   int64_t opt_timeout_ms_ = 20000;
   int64_t opt_one_shot_max_bytes_ = 256 << 10;
 

@@ -205,7 +205,9 @@ COS_API int cos_net_synchronize(cos_net* net);
 /* Options: "algo" (COS_ALGO_*), "zero_diff" (0/1, default 1),
  * "grid" (CTAs, 0 = auto), "block" (threads, 0 = auto), "kernel" (0 = LDG/STG
  * vector kernel, 1 = TMA bulk-copy pipeline), "barrier_timeout_ms",
- * "nvls" (0 = off, 1 = use multimem where available).  1/0. */
+ * "one_shot_max_bytes", "timing" (CUDA events around each launch),
+ * "initial_gather" (0 = connect() skips the first on_start(); the caller then
+ * runs cos_net_all_gather_weights itself).  1/0. */
 COS_API int cos_net_set_option(cos_net* net, const char* name, int64_t value);
 COS_API int64_t cos_net_get_option(cos_net* net, const char* name);
 

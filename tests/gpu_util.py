@@ -31,6 +31,9 @@ class Ranks:
             if devices is None and N > 1:
                 net.set_option("grid", grid)
                 net.set_option("block", block)
+                # launch the first on_start() from ONE thread (below) like every later step: kernels of
+                # in-process ranks launched from racing threads were not reliably co-scheduled
+                net.set_option("initial_gather", 0)
             for k, v in options.items():
                 net.set_option(k, v)
             self.nets.append(net)
@@ -54,6 +57,11 @@ class Ranks:
         with cf.ThreadPoolExecutor(self.N) as ex:
             res = list(ex.map(go, range(self.N)))
         assert all(ok for ok, _ in res), res
+        if self.nets[0].get_option("initial_gather") == 0:
+            for net in self.nets:
+                assert net.all_gather_weights(0), net.last_error()
+            for net in self.nets:
+                assert net.synchronize(), net.last_error()
 
     def step(self, grads):
         for net, g in zip(self.nets, grads):

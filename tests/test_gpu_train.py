@@ -59,10 +59,15 @@ def test_train_two_ranks_in_process(cos, oracle):
             n.set_option("grid", 8)
             n.set_option("block", 128)
             n.set_option("barrier_timeout_ms", 20000)
+            n.set_option("initial_gather", 0)
         prods = [harness.make_producer("cifar10_quick", n, seed=5) for n in netz]  # same init on both ranks
         table = [n.localAddresses() for n in netz]
         with cf.ThreadPoolExecutor(2) as ex:
             assert all(ex.map(lambda r: netz[r].connect([table[p][r] if p != r else "" for p in range(2)]), range(2)))
+        for n in netz:
+            assert n.all_gather_weights(0), n.last_error()
+        for n in netz:
+            assert n.synchronize(), n.last_error()
         rng = np.random.RandomState(1)
         batches = [(torch.from_numpy(rng.rand(100, 3, 32, 32).astype(np.float32)),
                     torch.from_numpy(rng.randint(0, 10, (100,)).astype(np.float32))) for _ in range(2)]
