@@ -27,6 +27,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 prints exactly ONE JSON line on stdout: keep NCCL's version banner off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 NVLINK_MEASURED_GBS = 770.0  # B200_PROFILING.md: measured peer copy per direction (900 nominal)
 HBM_FALLBACK_GBS = 6650.0    # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
@@ -482,8 +485,29 @@ def run_sweep(args):
                 t = torch.tensor([k], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 k = float(t.item())
+            # steady state: launches queued back to back on every rank (no host sync in between), so the
+            # host-side launch skew between ranks is not part of the number
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            st = torch.cuda.current_stream()
+            net.sync_step(0, st.cuda_stream)
+            a.record()
+            for _ in range(reps):
+                net.sync_step(0, st.cuda_stream)
+            b.record()
+            torch.cuda.synchronize()
+            if not net.synchronize():
+                raise RuntimeError(net.last_error())
+            piped = a.elapsed_time(b) / reps
+            if world > 1:
+                t = torch.tensor([piped], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                piped = float(t.item())
             row = {"bytes": S, "algo": {1: "two_shot", 2: "one_shot"}[algo] if world > 1 else "local",
-                   "kernel": "tma" if kern else "ldg", "kernel_ms": k, "min_ms": min(ms)}
+                   "kernel": "tma" if kern else "ldg", "kernel_ms": k, "min_ms": min(ms), "pipelined_ms": piped}
             if world > 1:
                 row["bus_gbs"] = S * 2 * (world - 1) / world / (k * 1e-3) / 1e9
             if world > 1 and nccl_ms is None:
