@@ -289,7 +289,7 @@ def run_ours(args):
                                f"PyTorch forward/backward + fused sync kernel",
                    "global_batch": world * batch, "parallelism": f"dp{world}",
                    "algo": {0: "local", 1: "two_shot", 2: "one_shot"}[mode], "grad_dtype": args.grad_dtype,
-                   "kernel": {0: "ldg_stg_vector", 1: "tma_bulk_pipeline"}[args.kernel],
+                   "kernel": {0: "ldg_stg_vector", 1: "tma_bulk_pipeline"}[int(net.get_option("resolved_kernel"))],
                    "producer": "cuda_graph" if graph is not None else "eager",
                    "l2": "flushed between steps (256 MiB write outside the timed events)" if need_flush
                          else f"working set {working_set >> 20} MiB > 126 MiB L2"},
@@ -300,8 +300,8 @@ def run_ours(args):
                 "last_loss": last_loss},
         "gpu_launches": int(launches), "e2e_gpu_launches": int(e2e_launches),
         "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fused_sync_sgd_tma_kernel" if args.kernel else
-                     "fused_sync_sgd_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": "fused_sync_sgd_tma_kernel" if
+                     int(net.get_option("resolved_kernel")) else "fused_sync_sgd_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes": alg, "peak_source": (peak_kind + " MEASURED_PEAKS.json hbm_gbs") if
                      world == 1 else "B200_PROFILING.md measured peer copy per direction"},
         "split_ms": {"forward_backward": fb_ms, "fused_sync_kernel": k_ms},
@@ -336,7 +336,7 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def kernel_rooflines(C, nets, peaks, world, kernel=0):
+def kernel_rooflines(C, nets, peaks, world, kernel=-1):
     """Fused-kernel-only timing of the three BASELINE layouts at N=1 (HBM roofline)."""
     import torch
     res = {}
@@ -415,16 +415,37 @@ def run_reference(args):
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
         mod = nets.torch_module(name).cuda()
+        for prm in mod.parameters():
+            prm.grad = torch.zeros_like(prm)
         c, h, w = nets.NETS[name]["input"]
         x = torch.rand((batch, c, h, w), device="cuda")
         y = torch.randint(0, nets.NETS[name]["classes"], (batch,), device="cuda")
         lossf = torch.nn.CrossEntropyLoss()
+
+        def fb():
+            lossf(mod(x), y).backward()
+
+        # same forward/backward execution as our arm (CUDA-graph replay) so that only the sync differs
+        run = fb
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fb()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fb()
+            run = graph.replay
+        except Exception:
+            run = fb
         evs = []
         for i in range(args.warmup + min(args.steps, 20)):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            mod.zero_grad(set_to_none=False)
-            lossf(mod(x), y).backward()
+            run()
             b.record()
             if i >= args.warmup:
                 evs.append((a, b))
@@ -549,7 +570,7 @@ def main():
     ap.add_argument("--workload", default="lenet", choices=["lenet", "cifar10_quick", "caffenet"])
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 two-shot, 2 one-shot")
-    ap.add_argument("--kernel", type=int, default=0, help="0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline")
+    ap.add_argument("--kernel", type=int, default=-1, help="-1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", action="store_true", default=True)

@@ -214,6 +214,15 @@ int CaffeNet::resolved_algo() const {
   return static_cast<int64_t>(count_ * sizeof(float)) <= opt_one_shot_max_bytes_ ? kModeOneShot : kModeTwoShot;
 }
 
+// Kernel variant: measured on B200 (profiles/r01_sweep_*.json) the TMA bulk-copy pipeline wins once the
+// message is large enough to be NVLink-bandwidth bound; the LDG/STG kernel has the lower fixed cost.
+// Depends only on (world, P), so every rank resolves the same variant.
+int CaffeNet::resolved_kernel() const {
+  if (opt_kernel_ >= 0) return opt_kernel_;
+  if (world_ == 1) return 0;
+  return count_ * sizeof(float) >= (2u << 20) ? 1 : 0;
+}
+
 float CaffeNet::current_rate() {
   int step = current_step_;
   float r = 0.f;
@@ -259,7 +268,7 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
   }
   if (world_ > 1) p.epoch = ++epoch_;
   if (opt_timing_) COS_RT(cudaEventRecord(ev_start_, stream));
-  cudaError_t e = (opt_kernel_ == 1 && mode != kModeAllGather)
+  cudaError_t e = (resolved_kernel() == 1 && mode != kModeAllGather)
                       ? launch_fused_sync_sgd_tma(p, opt_grid_, stream)
                       : launch_fused_sync_sgd(p, opt_grid_, opt_block_, stream);
   if (e != cudaSuccess) {
@@ -419,6 +428,7 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "grid") return opt_grid_;
   if (name == "block") return opt_block_;
   if (name == "kernel") return opt_kernel_;
+  if (name == "resolved_kernel") return resolved_kernel();
   if (name == "timing") return opt_timing_;
   if (name == "nvls") return opt_nvls_;
   if (name == "barrier_timeout_ms") return opt_timeout_ms_;

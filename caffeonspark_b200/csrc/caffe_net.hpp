@@ -78,6 +78,7 @@ class CaffeNet {
   bool launch(int mode, cudaStream_t stream, std::string* err);
   bool check_status(std::string* err);
   int resolved_algo() const;
+  int resolved_kernel() const;
 
   SolverSpec spec_;
   const int world_;
@@ -123,7 +124,7 @@ class CaffeNet {
   int opt_algo_ = COS_ALGO_AUTO;
   int opt_zero_diff_ = 1;
   int opt_grid_ = 0, opt_block_ = 0;
-  int opt_kernel_ = 0;
+  int opt_kernel_ = -1;  // -1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline
   int opt_timing_ = 1;
   int opt_nvls_ = 0;
   int opt_initial_gather_ = 1;  // connect() runs the first on_start() (all-gather of weight shards)

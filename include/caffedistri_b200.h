@@ -15,7 +15,7 @@
  * true/success and 0 for false/failure unless stated otherwise; integer
  * getters return -1 on failure (JN:235-249,479-580); the message behind a
  * failure is available from cos_last_error() (thread-local), which is what the
- * JNI shim turns into a java.lang.Exception (jni/common.cpp:111-116).
+ * JNI shim turns into a java.lang.Exception (src/main/cpp/common.cpp:111-116).
  * The handle is the value the reference stores in BaseObject.address (a long).
  *
  * There is NO CPU fallback: every compute entry point fails (0 / -1 with an
@@ -203,8 +203,8 @@ COS_API int cos_net_all_gather_weights(cos_net* net, int solver_index, void* cud
 COS_API int cos_net_synchronize(cos_net* net);
 
 /* Options: "algo" (COS_ALGO_*), "zero_diff" (0/1, default 1),
- * "grid" (CTAs, 0 = auto), "block" (threads, 0 = auto), "kernel" (0 = LDG/STG
- * vector kernel, 1 = TMA bulk-copy pipeline), "barrier_timeout_ms",
+ * "grid" (CTAs, 0 = auto), "block" (threads, 0 = auto), "kernel" (-1 = auto,
+ * 0 = LDG/STG vector kernel, 1 = TMA bulk-copy pipeline), "barrier_timeout_ms",
  * "one_shot_max_bytes", "timing" (CUDA events around each launch),
  * "initial_gather" (0 = connect() skips the first on_start(); the caller then
  * runs cos_net_all_gather_weights itself).  1/0. */

@@ -60,7 +60,7 @@ def test_train_two_ranks_in_process(cos, oracle):
             n.set_option("block", 128)
             n.set_option("barrier_timeout_ms", 20000)
             n.set_option("initial_gather", 0)
-        prods = [harness.make_producer("cifar10_quick", n, seed=5) for n in netz]  # same init on both ranks
+        prods = [harness.make_producer("cifar10_quick", n, seed=5, use_graph=False) for n in netz]  # same init on both ranks
         table = [n.localAddresses() for n in netz]
         with cf.ThreadPoolExecutor(2) as ex:
             assert all(ex.map(lambda r: netz[r].connect([table[p][r] if p != r else "" for p in range(2)]), range(2)))

@@ -152,3 +152,24 @@ def test_adapter_loopback_two_ranks_in_process(cos):
     with pytest.raises(cos.CosError, match="not offered"):
         ads[1].fetch_fd(0, "never-offered", timeout_ms=200)
     [a.close() for a in ads]
+
+
+def test_jni_shim_type_checks_and_covers_the_18_natives():
+    """No JDK here: the JNI shim is type-checked against a stand-in jni.h and
+    must define one Java_com_yahoo_ml_jcaffe_CaffeNet_* export per native the
+    reference's CaffeNet.java declares (CaffeNet.java:60-230)."""
+    import subprocess
+    src = os.path.join(ROOT, "caffeonspark_b200", "csrc", "jni_shim.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I",
+                        os.path.join(ROOT, "tests", "jni_stub"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    natives = ["allocate", "deallocate", "connect", "sync", "init", "predict", "train", "localAddresses", "deviceID",
+               "getInitIter", "getMaxIter", "getTestIter", "getTestInterval", "snapshot",
+               "getValidationOutputBlobNames", "getValidationOutputBlobs", "validation", "aggregateValidationOutputs"]
+    text = open(src).read()
+    for n in natives:
+        assert f"Java_com_yahoo_ml_jcaffe_CaffeNet_{n}(" in text, n
+    if os.path.isdir("/root/reference"):
+        java = open("/root/reference/caffe-distri/src/main/java/com/yahoo/ml/jcaffe/CaffeNet.java").read()
+        declared = set(re.findall(r"native\s+[\w\[\]]+\s+(\w+)\s*\(", java))
+        assert declared == set(natives), declared ^ set(natives)
