@@ -154,6 +154,7 @@ def run_ours(args):
     if args.algo:
         net.set_option("algo", args.algo)
     net.set_option("kernel", args.kernel)
+    net.set_option("nvls", int(args.nvls))
     net.set_option("barrier_timeout_ms", 60000)
     prod = harness.make_producer(name, net)
     cl.start()
@@ -290,6 +291,7 @@ def run_ours(args):
                    "global_batch": world * batch, "parallelism": f"dp{world}",
                    "algo": {0: "local", 1: "two_shot", 2: "one_shot"}[mode], "grad_dtype": args.grad_dtype,
                    "kernel": {0: "ldg_stg_vector", 1: "tma_bulk_pipeline"}[int(net.get_option("resolved_kernel"))],
+                   "nvls": bool(net.get_option("nvls_active")),
                    "producer": "cuda_graph" if graph is not None else "eager",
                    "l2": "flushed between steps (256 MiB write outside the timed events)" if need_flush
                          else f"working set {working_set >> 20} MiB > 126 MiB L2"},
@@ -480,12 +482,15 @@ def run_sweep(args):
     for S in sizes:
         P = S // 4
         variants = [(a, k) for a in ((1, 2) if (world > 1 and S <= (4 << 20)) else (1,)) for k in (0, 1)]
+        if world > 1 and args.nvls:
+            variants.append((1, 2))  # two-shot through NVLS (kernel id 2 = LDG kernel + multimem)
         nccl_ms = None
         for algo, kern in variants:
             desc = C.SolverDesc([P], lr_policy="fixed", base_lr=0.01, momentum=0.9, weight_decay=0.0005)
             cl = harness.Cluster(desc, rank=rank, world=world, device=local)
             net = cl.net
-            net.set_option("kernel", kern)
+            net.set_option("kernel", min(kern, 1) if kern != 2 else 0)
+            net.set_option("nvls", int(kern == 2))
             if world > 1:
                 net.set_option("algo", algo)
             net.set_option("barrier_timeout_ms", 60000)
@@ -528,7 +533,8 @@ def run_sweep(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 piped = float(t.item())
             row = {"bytes": S, "algo": {1: "two_shot", 2: "one_shot"}[algo] if world > 1 else "local",
-                   "kernel": "tma" if kern else "ldg", "kernel_ms": k, "min_ms": min(ms), "pipelined_ms": piped}
+                   "kernel": {0: "ldg", 1: "tma", 2: "nvls" if net.get_option("nvls_active") else "nvls-unavailable"}[kern],
+                   "kernel_ms": k, "min_ms": min(ms), "pipelined_ms": piped}
             if world > 1:
                 row["bus_gbs"] = S * 2 * (world - 1) / world / (k * 1e-3) / 1e9
             if world > 1 and nccl_ms is None:
@@ -571,6 +577,7 @@ def main():
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 two-shot, 2 one-shot")
     ap.add_argument("--kernel", type=int, default=-1, help="-1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline")
+    ap.add_argument("--nvls", action="store_true", help="reduce/broadcast through NVSwitch multicast (fp32 two-shot)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", action="store_true", default=True)

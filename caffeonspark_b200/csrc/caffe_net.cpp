@@ -218,6 +218,7 @@ int CaffeNet::resolved_algo() const {
 // message is large enough to be NVLink-bandwidth bound; the LDG/STG kernel has the lower fixed cost.
 // Depends only on (world, P), so every rank resolves the same variant.
 int CaffeNet::resolved_kernel() const {
+  if (nvls_active_ && spec_.grad_dtype == COS_GRAD_FP32 && resolved_algo() == kModeTwoShot) return 0;  // NVLS lives there
   if (opt_kernel_ >= 0) return opt_kernel_;
   if (world_ == 1) return 0;
   return count_ * sizeof(float) >= (2u << 20) ? 1 : 0;
@@ -248,6 +249,9 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
     p.wire[r] = peer_wire_[r];
     p.flags[r] = peer_flags_[r];
   }
+  p.use_nvls = nvls_active_ ? 1 : 0;
+  p.mc_data = nvls_active_ ? reinterpret_cast<float*>(mc_base_ + off_data_) : nullptr;
+  p.mc_diff = nvls_active_ ? reinterpret_cast<const float*>(mc_base_ + off_diff_) : nullptr;
   p.hist = hist_;
   p.seg_end = seg_end_;
   p.seg_lr_mult = seg_lr_;
@@ -431,6 +435,7 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "resolved_kernel") return resolved_kernel();
   if (name == "timing") return opt_timing_;
   if (name == "nvls") return opt_nvls_;
+  if (name == "nvls_active") return nvls_active_ ? 1 : 0;
   if (name == "barrier_timeout_ms") return opt_timeout_ms_;
   if (name == "one_shot_max_bytes") return opt_one_shot_max_bytes_;
   if (name == "initial_gather") return opt_initial_gather_;
@@ -557,8 +562,59 @@ NvlinkCaffeNet::~NvlinkCaffeNet() {
     std::string ignore;
     adapter_->barrier(2000, &ignore);
   }
+  mcast_.close();
   mappings_.clear();
   adapter_.reset();
+}
+
+void NvlinkCaffeNet::setup_nvls(int timeout_ms) {
+  nvls_active_ = false;
+  std::string e;
+  bool ok = arena_.transport() == kTransportVmmFd && MulticastMapping::supported(device_);
+  if (!ok) e = "multicast unsupported or arena not VMM-backed";
+  if (rank_ == 0) {
+    int fd = -1;
+    if (ok) ok = mcast_.create(device_, arena_.bytes(), world_, &fd, &e);
+    adapter_->offer("mcast", ok ? fd : -1, ok ? "1" : "0");
+    if (fd >= 0) close(fd);
+  } else {
+    int fd = -1;
+    std::string meta, fe;
+    bool got = adapter_->fetch(0, "mcast", &fd, &meta, timeout_ms, &fe);
+    if (!got || meta != "1" || fd < 0) {
+      if (fd >= 0) close(fd);
+      if (ok) e = got ? "rank 0 could not create the multicast object" : fe;
+      ok = false;
+    } else if (ok) {
+      ok = mcast_.import(device_, arena_.bytes(), fd, &e);
+    } else {
+      close(fd);
+    }
+  }
+  if (ok) ok = mcast_.add_device(&e);
+  // cuMulticastBindMem blocks until every device of the team was added: agree first
+  auto agree = [&](const char* key, bool mine) {
+    adapter_->offer(key, -1, mine ? "1" : "0");
+    bool all = mine;
+    for (int p = 0; p < world_; ++p) {
+      if (p == rank_) continue;
+      std::string meta, fe;
+      if (!adapter_->fetch(p, key, nullptr, &meta, timeout_ms, &fe) || meta != "1") all = false;
+    }
+    return all;
+  };
+  bool all = agree("mc_added", ok);
+  if (all) ok = mcast_.bind_and_map(arena_, &e);
+  all = agree("mc_mapped", all && ok);
+  if (all) {
+    nvls_active_ = true;
+    mc_base_ = static_cast<char*>(mcast_.base());
+    nvls_note_ = "nvls active";
+  } else {
+    mcast_.close();
+    nvls_note_ = "nvls off: " + (e.empty() ? std::string("a peer could not join the multicast team") : e);
+  }
+  if (getenv("COS_VERBOSE")) fprintf(stderr, "[caffedistri_b200] rank %d: %s\n", rank_, nvls_note_.c_str());
 }
 
 bool NvlinkCaffeNet::setup(int start_device_id, std::string* err) {
@@ -621,6 +677,7 @@ bool NvlinkCaffeNet::connect(const std::vector<std::string>& addresses, std::str
     peer_wire_[peer] = wire_ ? reinterpret_cast<uint16_t*>(base + off_wire_) : nullptr;
   }
   connected_ = true;
+  if (opt_nvls_) setup_nvls(timeout);
   // everyone has mapped everyone; then the first on_start(): all-gather of the
   // owners' weight shards (socket_sync_cpu.cpp:102-105), so that all ranks
   // start from the same weights even if they were initialised differently.

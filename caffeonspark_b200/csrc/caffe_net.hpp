@@ -110,6 +110,8 @@ class CaffeNet {
   const float* peer_hist_[kMaxRanks] = {};
   uint32_t* peer_flags_[kMaxRanks] = {};
   bool connected_ = false;
+  bool nvls_active_ = false;        // multicast object bound on every rank (NvlinkCaffeNet::setup_nvls)
+  char* mc_base_ = nullptr;         // multicast VA of the arena
 
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_start_ = nullptr, ev_stop_ = nullptr, ev_done_ = nullptr;
@@ -129,7 +131,9 @@ class CaffeNet {
   int opt_nvls_ = 0;
   int opt_initial_gather_ = 1;  // connect() runs the first on_start() (all-gather of weight shards)
   int64_t opt_timeout_ms_ = 20000;
-  int64_t opt_one_shot_max_bytes_ = 256 << 10;
+  // AUTO picks one-shot only below this size.  0: never -- on B200 two-shot was at least as fast at every
+  // measured size and world (profiles/r01_sweep_n2.json, r01_sweep_n8.json); one-shot stays selectable.
+  int64_t opt_one_shot_max_bytes_ = 0;
 
   cos_forward_backward_fn fb_fn_ = nullptr;
   void* fb_user_ = nullptr;
@@ -158,8 +162,14 @@ class NvlinkCaffeNet : public CaffeNet {
   bool sync(std::string* err) override;  // :497-504
 
  private:
+  // NVLS: cuMulticastCreate on rank 0, fd through the adapter, every rank adds its device, binds its
+  // arena and maps the multicast VA.  Non-fatal: stays off unless EVERY rank succeeded.
+  void setup_nvls(int timeout_ms);
+
   std::unique_ptr<PeerAdapter> adapter_;
   std::vector<std::unique_ptr<PeerMapping>> mappings_;
+  MulticastMapping mcast_;
+  std::string nvls_note_;
 };
 
 }  // namespace cosb

@@ -96,7 +96,10 @@ __device__ __forceinline__ float4 reduce_vec_any(const SyncParams& p, int s, uin
 // ------------------------------------------------------------- the kernel
 
 // N = compile-time world size (0 = runtime world, any size up to kMaxRanks).
-template <int N, bool BF16>
+// NVLS = reduce through the switch (multimem.ld_reduce) and broadcast the new
+// weights with one multicast store; the sum order is then the switch's, so the
+// result matches the reference to rounding (<= 1e-5 relative), not bit for bit.
+template <int N, bool BF16, bool NVLS = false>
 __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(const SyncParams p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_abort;
@@ -212,13 +215,21 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
             g.z = bf16_bits_to_float(float_to_bf16_bits(g.z));
             g.w = bf16_bits_to_float(float_to_bf16_bits(g.w));
           }
+        } else if (NVLS) {
+          const float4 sum = mc_ld_reduce(p.mc_diff + i);  // in-switch sum over all ranks, then the 1/N scale
+          g = make_float4(__fmul_rn(p.inv_scale, sum.x), __fmul_rn(p.inv_scale, sum.y),
+                          __fmul_rn(p.inv_scale, sum.z), __fmul_rn(p.inv_scale, sum.w));
         } else {
           g = reduce_vec_any<N, BF16>(p, s, i);
         }
         sgd_vec(p, cur, i, g, w, h);
         *reinterpret_cast<float4*>(hl + i) = h;
-        *reinterpret_cast<float4*>(wl + i) = w;
-        if (push) {
+        if (NVLS) {
+          mc_st(p.mc_data + i, w);  // one store: own data_ and every peer's data_
+        } else {
+          *reinterpret_cast<float4*>(wl + i) = w;
+        }
+        if (push && !NVLS) {
 #pragma unroll
           for (int q = 1; q < (N > 0 ? N : 1); ++q) {
             int dst = rank + q;
@@ -311,7 +322,9 @@ uint64_t host_mix64(uint64_t z) {
 
 template <int N>
 cudaError_t launch_n(const SyncParams& p, int grid, int block, size_t smem, cudaStream_t stream) {
-  if (p.grad_bf16) fused_sync_sgd_kernel<N, true><<<grid, block, smem, stream>>>(p);
+  if (N == 0 && p.use_nvls && p.mode == kModeTwoShot && !p.grad_bf16)
+    fused_sync_sgd_kernel<0, false, true><<<grid, block, smem, stream>>>(p);
+  else if (p.grad_bf16) fused_sync_sgd_kernel<N, true><<<grid, block, smem, stream>>>(p);
   else fused_sync_sgd_kernel<N, false><<<grid, block, smem, stream>>>(p);
   return cudaGetLastError();
 }
@@ -345,7 +358,8 @@ cudaError_t launch_fused_sync_sgd(const SyncParams& p, int grid, int block, cuda
   if (need < 1) need = 1;
   if (static_cast<uint64_t>(grid) > need) grid = static_cast<int>(need);
   size_t smem = p.nseg <= kMaxSegSmem ? static_cast<size_t>(p.nseg) * (sizeof(uint64_t) + 2 * sizeof(float)) : 0;
-  const int n = (p.mode == kModeLocal || p.mode == kModeAllGather) ? 0 : p.world;
+  const bool nvls = p.use_nvls && p.mode == kModeTwoShot && !p.grad_bf16 && p.mc_data && p.mc_diff;
+  const int n = (p.mode == kModeLocal || p.mode == kModeAllGather || nvls) ? 0 : p.world;
   switch (n) {
     case 2: return launch_n<2>(p, grid, block, smem, stream);
     case 3: return launch_n<3>(p, grid, block, smem, stream);

@@ -37,6 +37,9 @@ struct SyncParams {
   const float* diff[kMaxRanks];     // diff_ of every rank (fp32)
   uint16_t* wire[kMaxRanks];        // bf16 gradient wire buffer of every rank
   uint32_t* flags[kMaxRanks];       // flag region of every rank
+  float* mc_data;                   // NVLS: multicast address of data_ (a store lands on every rank)
+  const float* mc_diff;             // NVLS: multicast address of diff_ (a load returns the in-switch sum)
+  int use_nvls;                     // two-shot fp32 only: multimem.ld_reduce / multimem.st instead of P2P
   float* hist;                      // local SGD history (momentum buffer)
   const uint64_t* seg_end;          // [nseg] cumulative blob ends (exclusive)
   const float* seg_lr_mult;         // [nseg]

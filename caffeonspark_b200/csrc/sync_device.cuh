@@ -52,6 +52,24 @@ __device__ __forceinline__ void st_vec(float* p, const float4& v) {
                : "memory");
 }
 
+// NVLS (NVLink SHARP): one load on a multicast address returns the fp32 sum of the
+// word on every rank, reduced inside the NVSwitch (SASS LDGMC.E.ADD.F32x4); one
+// store on it lands on every rank.
+__device__ __forceinline__ float4 mc_ld_reduce(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void mc_st(float* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
 
 __device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {

@@ -120,8 +120,9 @@ def test_generic_world_size_and_odd_shapes(cos, oracle):
 def test_auto_algo_switch_is_size_based(cos):
     small = cos.SolverDesc([1000], **HP)
     big = cos.SolverDesc([1 << 20], **HP)
-    for desc, want in ((small, 2), (big, 1)):
+    for desc, threshold, want in ((small, 0, 1), (small, 256 << 10, 2), (big, 256 << 10, 1)):
         net = cos.CaffeNet(desc, "", "", 1, 2, 0, True, cos.CaffeNet.SOCKET, -1, 0)
+        net.set_option("one_shot_max_bytes", threshold)  # default 0: two-shot everywhere (measured faster)
         assert net.get_option("resolved_algo") == want
         net.deallocate()
 

@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0):
+def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0, nvls=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     dev = 0 if shared_gpu else rank
@@ -50,6 +50,7 @@ def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0):
         net = cl.net
         net.set_option("algo", algo)
         net.set_option("kernel", kernel)
+        net.set_option("nvls", int(nvls))
         net.set_option("barrier_timeout_ms", 60000 if shared_gpu else 15000)
         if shared_gpu:  # contexts time-slice on the one GPU: keep the spinning grids tiny
             net.set_option("grid", 2)
@@ -65,11 +66,18 @@ def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0):
             torch.cuda.synchronize()
             assert net.sync_step(0), net.last_error()
             assert net.synchronize(), net.last_error()
-            ok = ok and np.array_equal(to_host(net.data()).view(np.uint32), sim.consistent_weights().view(np.uint32))
             o, s = net.shard()
-            ok = ok and np.array_equal(to_host(net.history())[o:o + s].view(np.uint32),
-                                       sim.consistent_history()[o:o + s].view(np.uint32))
-        q.put((rank, bool(ok), int(net.get_option("transport")), float(net.last_kernel_ms())))
+            if nvls and net.get_option("nvls_active") == 1:
+                # the switch chooses the summation order: north-star tolerance, not bit equality
+                ok = ok and np.allclose(to_host(net.data()), sim.consistent_weights(), rtol=1e-5, atol=1e-8)
+                ok = ok and np.allclose(to_host(net.history())[o:o + s], sim.consistent_history()[o:o + s],
+                                        rtol=1e-5, atol=1e-9)
+            else:
+                ok = ok and np.array_equal(to_host(net.data()).view(np.uint32),
+                                           sim.consistent_weights().view(np.uint32))
+                ok = ok and np.array_equal(to_host(net.history())[o:o + s].view(np.uint32),
+                                           sim.consistent_history()[o:o + s].view(np.uint32))
+        q.put((rank, bool(ok), int(net.get_option("nvls_active")), float(net.last_kernel_ms())))
         assert net.sync()
         net.deallocate()
     finally:
@@ -94,6 +102,31 @@ def test_one_process_per_gpu_bit_exact(cos, oracle, algo, bf16, kernel):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     res = sorted(q.get(timeout=5) for _ in range(world))
     assert all(ok for _, ok, _, _ in res), res
+
+
+@pytest.mark.skipif(gpu_count() < 2, reason="needs >= 2 GPUs")
+def test_nvls_two_shot_within_tolerance(cos, oracle):
+    """NVLS variant (multimem.ld_reduce / multimem.st through the NVSwitch): the
+    in-switch summation order is unspecified, so the bar is the north star's
+    1e-5 relative.  If the platform does not expose multicast the library keeps
+    the P2P path (then the result must be bit-exact) -- reported, not failed."""
+    import torch.multiprocessing as mp
+    world = min(gpu_count(), 8)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 1, False, q, False, 0, True)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert all(ok for _, ok, _, _ in res), res
+    active = {a for _, _, a, _ in res}
+    assert len(active) == 1, "ranks disagree on whether NVLS is active"
+    print("NVLS active:", active)
 
 
 @pytest.mark.skipif(gpu_count() < 1, reason="needs a GPU")
