@@ -176,6 +176,14 @@ def run_ours(args):
         if need_flush:
             flush_buf.zero_()
 
+    # Everything below runs on ONE explicit stream.  (torch's default stream has the handle 0, which the
+    # C ABI reads as "use the net's own stream": forward/backward and the sync launch would then sit on
+    # two unordered streams and the sync kernel would fall outside the timed events.)
+    work = torch.cuda.Stream()
+    work.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(work)
+    assert torch.cuda.current_stream().cuda_stream != 0
+
     # Net::ForwardBackward, captured in a CUDA graph when possible (launch-bound for the small nets)
     graph = None
     if not args.no_graph:
@@ -518,12 +526,15 @@ def run_sweep(args):
                 dist.barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 20
-            st = torch.cuda.current_stream()
-            net.sync_step(0, st.cuda_stream)
-            a.record()
-            for _ in range(reps):
-                net.sync_step(0, st.cuda_stream)
-            b.record()
+            st = torch.cuda.Stream()  # explicit stream: handle 0 would mean "the net's own stream"
+            with torch.cuda.stream(st):
+                if not net.sync_step(0, st.cuda_stream):
+                    raise RuntimeError(net.last_error())
+                a.record()
+                for _ in range(reps):
+                    if not net.sync_step(0, st.cuda_stream):
+                        raise RuntimeError(net.last_error())
+                b.record()
             torch.cuda.synchronize()
             if not net.synchronize():
                 raise RuntimeError(net.last_error())
