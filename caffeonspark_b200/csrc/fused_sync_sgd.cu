@@ -202,7 +202,34 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
         r = shard_range(p.count, world, s);
       }
       if (tid < r.nvec) cur.seek((r.vec_lo + tid) << 2);
-      for (uint64_t j = tid; j < r.nvec; j += stride) {
+      if (NVLS) {
+        // switch loads have the longest latency on the path: keep kNvlsUnroll of them (plus the local w/h
+        // loads) in flight per thread.  j and j + u*stride belong to the same CTA, so the partition holds.
+        constexpr int kNvlsUnroll = 4;
+        for (uint64_t j0 = tid; j0 < r.nvec; j0 += stride * kNvlsUnroll) {
+          float4 sum[kNvlsUnroll];
+#pragma unroll
+          for (int u = 0; u < kNvlsUnroll; ++u) {
+            const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
+            if (j < r.nvec) sum[u] = mc_ld_reduce(p.mc_diff + ((r.vec_lo + j) << 2));
+          }
+#pragma unroll
+          for (int u = 0; u < kNvlsUnroll; ++u) {
+            const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
+            if (j < r.nvec) {
+              const uint64_t i = (r.vec_lo + j) << 2;
+              float4 w = *reinterpret_cast<const float4*>(wl + i);  // local: short latency, hidden by the other warps
+              float4 h = *reinterpret_cast<const float4*>(hl + i);
+              const float4 g = make_float4(__fmul_rn(p.inv_scale, sum[u].x), __fmul_rn(p.inv_scale, sum[u].y),
+                                           __fmul_rn(p.inv_scale, sum[u].z), __fmul_rn(p.inv_scale, sum[u].w));
+              sgd_vec(p, cur, i, g, w, h);
+              *reinterpret_cast<float4*>(hl + i) = h;
+              mc_st(p.mc_data + i, w);  // one store: own data_ and every peer's data_
+            }
+          }
+        }
+      }
+      for (uint64_t j = NVLS ? r.nvec : tid; j < r.nvec; j += stride) {
         const uint64_t i = (r.vec_lo + j) << 2;
         float4 w = *reinterpret_cast<const float4*>(wl + i);
         float4 h = *reinterpret_cast<const float4*>(hl + i);
