@@ -487,6 +487,7 @@ def run_sweep(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     rows = []
     sizes = [64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20, 512 << 20]
+    sizes = [b for b in sizes if args.sweep_min_bytes <= b <= args.sweep_max_bytes]
     for S in sizes:
         P = S // 4
         variants = [(a, k) for a in ((1, 2) if (world > 1 and S <= (4 << 20)) else (1,)) for k in (0, 1)]
@@ -594,6 +595,8 @@ def main():
     ap.add_argument("--kernels", action="store_true", default=True)
     ap.add_argument("--no-kernels", dest="kernels", action="store_false")
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--sweep-min-bytes", type=int, default=0)
+    ap.add_argument("--sweep-max-bytes", type=int, default=1 << 40)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
