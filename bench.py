@@ -547,6 +547,20 @@ def run_sweep(args):
             row = {"bytes": S, "algo": {1: "two_shot", 2: "one_shot"}[algo] if world > 1 else "local",
                    "kernel": {0: "ldg", 1: "tma", 2: "nvls" if net.get_option("nvls_active") else "nvls-unavailable"}[kern],
                    "kernel_ms": k, "min_ms": min(ms), "pipelined_ms": piped}
+            if args.trace and kern == 0:
+                # where the time goes inside one launch (CTA 0, %globaltimer): launch->A, A->phase1 end, B, zero
+                net.set_option("trace", 1)
+                tr = []
+                for _ in range(5):
+                    torch.cuda.synchronize()
+                    if world > 1:
+                        dist.barrier()
+                    net.sync_step(0)
+                    net.synchronize()
+                    t = [net.get_option(f"trace_{i}") for i in range(5)]
+                    tr.append([(t[i + 1] - t[i]) / 1e3 for i in range(4)])
+                net.set_option("trace", 0)
+                row["trace_us_barrierA_phase1_barrierB_zero"] = [sorted(c)[len(c) // 2] for c in zip(*tr)]
             if world > 1:
                 row["bus_gbs"] = S * 2 * (world - 1) / world / (k * 1e-3) / 1e9
             if world > 1 and nccl_ms is None:
@@ -595,6 +609,7 @@ def main():
     ap.add_argument("--kernels", action="store_true", default=True)
     ap.add_argument("--no-kernels", dest="kernels", action="store_false")
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="sweep: per-phase timestamps of the LDG kernel")
     ap.add_argument("--sweep-min-bytes", type=int, default=0)
     ap.add_argument("--sweep-max-bytes", type=int, default=1 << 40)
     args = ap.parse_args()

@@ -181,8 +181,9 @@ bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::str
   COS_RT(cudaMemcpy(seg_lr_, lr.data(), nseg_ * sizeof(float), cudaMemcpyHostToDevice));
   COS_RT(cudaMemcpy(seg_dm_, dm.data(), nseg_ * sizeof(float), cudaMemcpyHostToDevice));
 
-  COS_RT(cudaHostAlloc(reinterpret_cast<void**>(&status_), sizeof(int), cudaHostAllocMapped));
-  *status_ = 0;
+  // host-mapped: [0] device-side error word, [2..11] optional phase timestamps (option "trace")
+  COS_RT(cudaHostAlloc(reinterpret_cast<void**>(&status_), 16 * sizeof(unsigned long long), cudaHostAllocMapped));
+  memset(status_, 0, 16 * sizeof(unsigned long long));
   COS_RT(cudaMalloc(reinterpret_cast<void**>(&loss_dev_), sizeof(float)));
   COS_RT(cudaMemset(loss_dev_, 0, sizeof(float)));
   COS_RT(cudaHostAlloc(reinterpret_cast<void**>(&loss_host_), sizeof(float), cudaHostAllocDefault));
@@ -261,6 +262,7 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
   p.inv_scale = static_cast<float>(1.0 / static_cast<double>(world_));  // Dtype(1.0 / solver_count)
   p.timeout_ns = static_cast<unsigned long long>(opt_timeout_ms_) * 1000000ull;
   p.status = status_;
+  p.trace = opt_trace_ ? reinterpret_cast<unsigned long long*>(status_) + 2 : nullptr;
   if (mode != kModeAllGather) {
     if (!learning_rate(spec_.lr_policy, spec_.base_lr, spec_.gamma, spec_.power, spec_.stepsize,
                        spec_.stepvalues.empty() ? nullptr : spec_.stepvalues.data(),
@@ -418,6 +420,7 @@ bool CaffeNet::set_option(const std::string& name, int64_t v, std::string* err) 
   else if (name == "one_shot_max_bytes") opt_one_shot_max_bytes_ = v;
   else if (name == "iter") { iter_ = static_cast<int>(v); }
   else if (name == "initial_gather") opt_initial_gather_ = v != 0;
+  else if (name == "trace") opt_trace_ = v != 0;
   else {
     *err = "unknown option '" + name + "'";
     return false;
@@ -439,6 +442,8 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "barrier_timeout_ms") return opt_timeout_ms_;
   if (name == "one_shot_max_bytes") return opt_one_shot_max_bytes_;
   if (name == "initial_gather") return opt_initial_gather_;
+  if (name.compare(0, 6, "trace_") == 0 && name.size() == 7 && name[6] >= '0' && name[6] <= '4')
+    return static_cast<int64_t>((reinterpret_cast<volatile unsigned long long*>(status_) + 2)[name[6] - '0']);
   if (name == "transport") return arena_.transport();
   if (name == "default_grid") return default_sync_grid(device_);
   return -1;

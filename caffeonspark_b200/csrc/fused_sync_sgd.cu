@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
   cur.nseg = p.nseg;
   cur.k = 0;
 
+  const bool tracer = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tracer) p.trace[0] = globaltimer_ns();
   const int world = (N > 0) ? N : p.world;
   const int rank = p.rank;
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
   if (multi) {
     if (!cta_barrier(p, 0, &s_abort)) return;
   }
+  if (tracer) p.trace[1] = globaltimer_ns();
 
   // ---- phase 1 ------------------------------------------------------------
   if (p.mode == kModeAllGather) {
@@ -300,9 +303,11 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
   }
 
   // ---- barrier B: peers finished reading my diff_, their pushes landed ----
+  if (tracer) p.trace[2] = globaltimer_ns();
   if (multi) {
     if (!cta_barrier(p, 1, &s_abort)) return;
   }
+  if (tracer) p.trace[3] = globaltimer_ns();
 
   // ---- phase 2: ClearParamDiffs of the next Step --------------------------
   if (p.zero_diff && p.mode != kModeAllGather) {
@@ -324,6 +329,7 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
       }
     }
   }
+  if (tracer) p.trace[4] = globaltimer_ns();
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
