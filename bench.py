@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -217,6 +217,17 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_end = time.perf_counter() + 0.4  # nvidia-smi needs a moment to emit its first rows: same load meanwhile
+    spin = torch.tensor([1], device="cuda")
+    while True:                        # collective: every rank runs the same number of extra steps
+        for _ in range(10):
+            step()
+        spin[0] = 1 if time.perf_counter() < t_end else 0
+        if world > 1:
+            dist.all_reduce(spin, op=dist.ReduceOp.MIN)
+        if int(spin.item()) == 0:
+            break
+    torch.cuda.synchronize()
     launches0 = net.launch_count()
     total_ms = cuda_time_steps(torch, dist, world, args.steps, args.warmup, step, flush)
     launches = net.launch_count() - launches0 - args.warmup
@@ -384,7 +395,7 @@ def cpu_baseline(name, desc, batch, world, fb_ms):
     # ~10-20 s of CPU work: measured rates are ~0.4 GB/s (socket path) / ~2 GB/s (local update)
     if O.ref_available():
         est_ms = max(0.5, 4 * P / 1e6 * (4.0 if world > 1 else 1.0) * world)
-        iters = int(max(4, min(200, 15000 / est_ms)))
+        iters = int(max(4, min(2000, 10000 / est_ms)))  # ~10 s of CPU work, bounded
         r = O.run_ref_time(world, desc.counts, desc.lr_mult, desc.decay_mult, iters=iters, **desc.hyper())
         sync_ms, kind = r["ms_per_iter_median"], "reference"
         used = world  # one solver thread per executor process (+ its receiver threads)

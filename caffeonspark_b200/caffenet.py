@@ -139,7 +139,7 @@ class CaffeNet:
         self._L = _lib.lib()
         self._h = ctypes.c_void_p()
         self._fb_keep = None
-        self.cluster_size, self.node_rank = cluster_size, node_rank
+        self.cluster_size, self.node_rank, self.num_local_devices = cluster_size, node_rank, num_local_devices
         if isinstance(solver_conf_file, SolverDesc):
             self.desc = solver_conf_file
             d, keep = self.desc.to_c()
@@ -258,23 +258,27 @@ class CaffeNet:
     def history_ptr(self, solver_index=0):
         return self._L.cos_net_history(self._h, solver_index)
 
-    def _torch_view(self, ptr):
+    def _torch_view(self, ptr, solver_index=0):
         import torch
-        return torch.as_tensor(_DevArray(ptr, self.param_count()), device=f"cuda:{self.deviceID(0)}")
+        return torch.as_tensor(_DevArray(ptr, self.param_count()), device=f"cuda:{self.deviceID(solver_index)}")
 
-    def data(self):
-        """Zero-copy torch view of Params::data_ (flat fp32 weights)."""
-        return self._torch_view(self.data_ptr())
+    def data(self, solver_index=0):
+        """Zero-copy torch view of Params::data_ (flat fp32 weights) of local solver `solver_index`."""
+        return self._torch_view(self.data_ptr(solver_index), solver_index)
 
-    def diff(self):
-        return self._torch_view(self.diff_ptr())
+    def diff(self, solver_index=0):
+        return self._torch_view(self.diff_ptr(solver_index), solver_index)
 
-    def history(self):
-        return self._torch_view(self.history_ptr())
+    def history(self, solver_index=0):
+        return self._torch_view(self.history_ptr(solver_index), solver_index)
+
+    def global_rank(self, solver_index=0):
+        """Rank of local solver `solver_index` in the collective of cluster_size x num_local_devices ranks."""
+        return self.node_rank * self.num_local_devices + solver_index
 
     def shard(self, rank=None):
         o, s = ctypes.c_uint64(), ctypes.c_uint64()
-        if not self._L.cos_net_shard(self._h, self.node_rank if rank is None else rank, ctypes.byref(o),
+        if not self._L.cos_net_shard(self._h, self.global_rank(0) if rank is None else rank, ctypes.byref(o),
                                      ctypes.byref(s)):
             raise CosError(_err())
         return o.value, s.value

@@ -40,14 +40,23 @@ CaffeNet* CaffeNet::create(const SolverSpec& spec, int num_local_devices, int cl
     *err = "number of local Devices must be greater than or equal to 1";
     return nullptr;
   }
-  if (num_local_devices != 1) {
-    *err = "num_local_devices > 1 inside one executor is not supported yet: run one executor per GPU "
-           "(-devices 1 -clusterSize N)";
+  if (cluster_size < 1 || num_local_devices > kMaxRanks || cluster_size * num_local_devices > kMaxRanks) {
+    *err = "cluster_size x num_local_devices must be in [1, " + std::to_string(kMaxRanks) + "]";
     return nullptr;
   }
-  if (cluster_size < 1 || cluster_size > kMaxRanks) {
-    *err = "cluster size must be in [1, " + std::to_string(kMaxRanks) + "]";
-    return nullptr;
+  if (num_local_devices > 1) {  // -devices k: every local GPU is a rank of one collective (row f2)
+    if (node_rank < 0 || node_rank >= cluster_size) {
+      *err = "node_rank out of range";
+      return nullptr;
+    }
+    if (cluster_size > 1 && connection_type != COS_CONNECTION_RDMA && connection_type != COS_CONNECTION_SOCKET) {
+      *err = "unable to create CaffeNet object";
+      return nullptr;
+    }
+    std::unique_ptr<MultiDeviceCaffeNet> n(
+        new MultiDeviceCaffeNet(spec, num_local_devices, cluster_size, node_rank, is_training));
+    if (!n->setup(start_device_id, err)) return nullptr;
+    return n.release();
   }
   if (cluster_size == 1) {  // JniCaffeNet.cpp:42-46
     std::unique_ptr<LocalCaffeNet> n(new LocalCaffeNet(spec, is_training));
@@ -115,6 +124,10 @@ bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::str
       break;
     }
     cudaGetLastError();
+  }
+  if (dev < 0 && getenv("COS_ALLOW_SHARED_DEVICE") && start_device_id >= 0 && start_device_id < ndev &&
+      cudaSetDevice(start_device_id) == cudaSuccess) {
+    dev = start_device_id;  // tests on a single-GPU box: several local "devices" share the last GPU
   }
   if (dev < 0) {
     *err = "cannot grab GPU device after id " + std::to_string(start_device_id);
@@ -394,7 +407,7 @@ bool CaffeNet::train(int solver_index, const cos_blob* data, int ndata, std::str
     dev_blobs[i] = data[i];
     dev_blobs[i].data = static_cast<const float*>(in_dev_[i]);
   }
-  int rc = fb_fn_(fb_user_, solver_index, dev_blobs.data(), ndata, loss_dev_, stream_);
+  int rc = fb_fn_(fb_user_, solver_index_, dev_blobs.data(), ndata, loss_dev_, stream_);
   if (rc != 0) {
     *err = "gradient producer failed with code " + std::to_string(rc);
     return false;
@@ -700,6 +713,135 @@ bool NvlinkCaffeNet::connect(const std::vector<std::string>& addresses, std::str
 
 bool NvlinkCaffeNet::sync(std::string* err) {
   if (world_ > 1) return adapter_->barrier(static_cast<int>(opt_timeout_ms_), err);
+  return true;
+}
+
+}  // namespace cosb
+
+// ------------------------------------------------------ MultiDeviceCaffeNet
+namespace cosb {
+
+MultiDeviceCaffeNet::MultiDeviceCaffeNet(const SolverSpec& spec, int num_local_devices, int cluster_size,
+                                         int node_rank, bool is_training)
+    : CaffeNet(spec, cluster_size * num_local_devices, node_rank * num_local_devices, is_training),
+      executors_(cluster_size),
+      node_rank_(node_rank) {
+  for (int i = 0; i < num_local_devices; ++i) {
+    ranks_.emplace_back(new NvlinkCaffeNet(spec, cluster_size * num_local_devices, node_rank * num_local_devices + i,
+                                           is_training));
+    ranks_.back()->set_solver_index(i);
+  }
+}
+
+MultiDeviceCaffeNet::~MultiDeviceCaffeNet() {
+  // the ranks rendezvous with their peers while shutting down: tear them down concurrently
+  std::vector<std::thread> th;
+  for (auto& r : ranks_) th.emplace_back([&r] { r.reset(); });
+  for (auto& t : th) t.join();
+}
+
+bool MultiDeviceCaffeNet::setup(int start_device_id, std::string* err) {
+  int d = start_device_id;  // CaffeNet.cpp:130-142: d = FindDevice(d + 1) for each local device in turn
+  for (auto& r : ranks_) {
+    if (!r->setup(d, err)) return false;
+    d = r->device();
+  }
+  return true;
+}
+
+void MultiDeviceCaffeNet::localAddresses(std::vector<std::string>* vec) {
+  std::string mine;
+  for (size_t i = 0; i < ranks_.size(); ++i) {
+    std::vector<std::string> a;
+    ranks_[i]->localAddresses(&a);
+    // every entry of a rank's list except its own is the same endpoint
+    const std::string& ep = a[(ranks_[i]->rank() + 1) % a.size()];
+    mine += (i ? ";" : "") + ep;
+  }
+  vec->assign(executors_, std::string());
+  for (int e = 0; e < executors_; ++e)
+    if (e != node_rank_) (*vec)[e] = mine;  // "" at the own rank (CaffeNet.cpp:398-401)
+}
+
+bool MultiDeviceCaffeNet::connect(const std::vector<std::string>& addresses, std::string* err) {
+  const int k = static_cast<int>(ranks_.size());
+  if (executors_ > 1 && static_cast<int>(addresses.size()) < executors_) {
+    *err = "connect: need " + std::to_string(executors_) + " addresses, got " + std::to_string(addresses.size());
+    return false;
+  }
+  std::vector<std::string> table(static_cast<size_t>(executors_) * k);
+  for (int e = 0; e < executors_; ++e) {
+    if (e == node_rank_) {
+      for (int i = 0; i < k; ++i) {
+        std::vector<std::string> a;
+        ranks_[i]->localAddresses(&a);
+        table[static_cast<size_t>(e) * k + i] = a[(ranks_[i]->rank() + 1) % a.size()];
+      }
+      continue;
+    }
+    std::string rest = addresses[e];
+    for (int i = 0; i < k; ++i) {
+      size_t semi = rest.find(';');
+      if ((i < k - 1) == (semi == std::string::npos) || rest.empty()) {
+        *err = "connect: executor " + std::to_string(e) + " did not publish " + std::to_string(k) +
+               " device endpoints: '" + addresses[e] + "'";
+        return false;
+      }
+      table[static_cast<size_t>(e) * k + i] = rest.substr(0, semi);
+      rest = semi == std::string::npos ? "" : rest.substr(semi + 1);
+    }
+  }
+  // every rank's connect() rendezvouses with all the others, local ones included: run them concurrently
+  std::vector<std::string> errs(k);
+  std::vector<char> ok(k, 0);
+  std::vector<std::thread> th;
+  for (int i = 0; i < k; ++i) th.emplace_back([&, i] { ok[i] = ranks_[i]->connect(table, &errs[i]) ? 1 : 0; });
+  for (auto& t : th) t.join();
+  for (int i = 0; i < k; ++i) {
+    if (!ok[i]) {
+      *err = "local device " + std::to_string(i) + ": " + errs[i];
+      return false;
+    }
+  }
+  connected_ = true;
+  return true;
+}
+
+bool MultiDeviceCaffeNet::sync(std::string* err) {
+  const int k = static_cast<int>(ranks_.size());
+  std::vector<std::string> errs(k);
+  std::vector<char> ok(k, 0);
+  std::vector<std::thread> th;
+  for (int i = 0; i < k; ++i) th.emplace_back([&, i] { ok[i] = ranks_[i]->sync(&errs[i]) ? 1 : 0; });
+  for (auto& t : th) t.join();
+  for (int i = 0; i < k; ++i) {
+    if (!ok[i]) {
+      *err = errs[i];
+      return false;
+    }
+  }
+  return true;
+}
+
+bool MultiDeviceCaffeNet::synchronize(std::string* err) {
+  for (auto& r : ranks_)
+    if (!r->synchronize(err)) return false;
+  return true;
+}
+
+void MultiDeviceCaffeNet::set_forward_backward(cos_forward_backward_fn fn, void* user) {
+  for (auto& r : ranks_) r->set_forward_backward(fn, user);
+}
+
+int64_t MultiDeviceCaffeNet::launch_count() const {
+  int64_t n = 0;
+  for (auto& r : ranks_) n += r->launch_count();
+  return n;
+}
+
+bool MultiDeviceCaffeNet::set_option(const std::string& name, int64_t v, std::string* err) {
+  for (auto& r : ranks_)
+    if (!r->set_option(name, v, err)) return false;
   return true;
 }
 

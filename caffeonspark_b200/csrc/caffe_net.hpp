@@ -38,10 +38,15 @@ class CaffeNet {
   virtual bool connect(const std::vector<std::string>& addresses, std::string* err) = 0;
   virtual bool sync(std::string* err) { (void)err; return true; }  // CaffeNet.hpp:91
 
+  // The object that serves local solver `solver_index` (one per local device, CaffeNet.hpp syncs_[i]);
+  // a single-device net serves index 0 itself.
+  virtual CaffeNet* rank_net(int solver_index) { return solver_index == 0 ? this : nullptr; }
+  virtual int num_local_devices() const { return 1; }
+
   int deviceID(int solver_index) const;
   bool init(int solver_index, bool enable_nn, std::string* err);
   bool train(int solver_index, const cos_blob* data, int ndata, std::string* err);
-  int snapshot(std::string* err);
+  virtual int snapshot(std::string* err);
   // resume from files written by snapshot() (CaffeNet.cpp:198-205 restore path)
   bool restore(const std::string& model_file, const std::string& state_file, std::string* err);
   int getInitIter(int solver_index) const { return solver_index == 0 ? spec_.init_iter : -1; }
@@ -52,9 +57,10 @@ class CaffeNet {
   // hot path
   bool sync_step(int solver_index, cudaStream_t stream, bool use_own_stream, std::string* err);
   bool all_gather_weights(cudaStream_t stream, bool use_own_stream, std::string* err);
-  bool synchronize(std::string* err);
+  virtual bool synchronize(std::string* err);
 
-  void set_forward_backward(cos_forward_backward_fn fn, void* user) { fb_fn_ = fn; fb_user_ = user; }
+  virtual void set_forward_backward(cos_forward_backward_fn fn, void* user) { fb_fn_ = fn; fb_user_ = user; }
+  void set_solver_index(int i) { solver_index_ = i; }
   float* data() const { return data_; }
   float* diff() const { return diff_; }
   float* history() const { return hist_; }
@@ -65,9 +71,10 @@ class CaffeNet {
   float current_rate();
   float last_loss() const { return last_loss_; }
   float last_kernel_ms();
-  int64_t launch_count() const { return launches_; }
-  bool set_option(const std::string& name, int64_t v, std::string* err);
-  int64_t get_option(const std::string& name) const;
+  virtual int64_t launch_count() const { return launches_; }
+  virtual bool set_option(const std::string& name, int64_t v, std::string* err);
+  virtual int64_t get_option(const std::string& name) const;
+  int device() const { return device_; }
   const SolverSpec& spec() const { return spec_; }
   const std::vector<const char*>& address_cstrs() { return addr_cstrs_; }
   std::vector<std::string>& address_store() { return addr_store_; }
@@ -138,6 +145,7 @@ class CaffeNet {
 
   cos_forward_backward_fn fb_fn_ = nullptr;
   void* fb_user_ = nullptr;
+  int solver_index_ = 0;  // index the gradient producer sees (local device number inside the executor)
   std::vector<void*> in_dev_;       // staged input blobs
   std::vector<size_t> in_bytes_;
   std::vector<std::string> addr_store_;
@@ -171,6 +179,37 @@ class NvlinkCaffeNet : public CaffeNet {
   std::vector<std::unique_ptr<PeerMapping>> mappings_;
   MulticastMapping mcast_;
   std::string nvls_note_;
+};
+
+// `-devices k` inside one executor.  The reference reduces the k local GPUs with a
+// P2PSync tree and lets only the root GPU talk to other executors (parallel.cpp:202-418, CaffeNet.cpp:456-480);
+// here every local GPU is a first-class rank of ONE collective of cluster_size*k ranks (rank = node_rank*k + i),
+// so the tree, its extra D2D copies and the root bottleneck disappear.  Executor-level address strings carry
+// the k per-device endpoints joined with ';'.
+class MultiDeviceCaffeNet : public CaffeNet {
+ public:
+  MultiDeviceCaffeNet(const SolverSpec& spec, int num_local_devices, int cluster_size, int node_rank,
+                      bool is_training);
+  ~MultiDeviceCaffeNet() override;
+  bool setup(int start_device_id, std::string* err);
+  void localAddresses(std::vector<std::string>* vec) override;
+  bool connect(const std::vector<std::string>& addresses, std::string* err) override;
+  bool sync(std::string* err) override;
+  CaffeNet* rank_net(int solver_index) override {
+    return (solver_index >= 0 && solver_index < static_cast<int>(ranks_.size())) ? ranks_[solver_index].get() : nullptr;
+  }
+  int num_local_devices() const override { return static_cast<int>(ranks_.size()); }
+  int snapshot(std::string* err) override { return ranks_[0]->snapshot(err); }
+  bool synchronize(std::string* err) override;
+  void set_forward_backward(cos_forward_backward_fn fn, void* user) override;
+  int64_t launch_count() const override;
+  bool set_option(const std::string& name, int64_t v, std::string* err) override;
+  int64_t get_option(const std::string& name) const override { return ranks_[0]->get_option(name); }
+
+ private:
+  const int executors_;
+  const int node_rank_;
+  std::vector<std::unique_ptr<NvlinkCaffeNet>> ranks_;
 };
 
 }  // namespace cosb

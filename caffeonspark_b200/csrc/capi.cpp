@@ -27,6 +27,8 @@ int fail(const std::string& msg, int rc = 0) {
 }
 
 CaffeNet* N(cos_net* n) { return reinterpret_cast<CaffeNet*>(n); }
+// the object serving local solver `i` (one per local device); nullptr for an invalid index
+CaffeNet* R(cos_net* n, int i) { return (n && i >= 0) ? reinterpret_cast<CaffeNet*>(n)->rank_net(i) : nullptr; }
 
 // common.cpp:111-116 ThrowJavaException analogue: never let a C++ exception
 // cross the C boundary.
@@ -178,7 +180,9 @@ int cos_net_init(cos_net* net, int solver_index, int enable_nn) {
     if (!net) return fail("net is NULL");
     if (solver_index < 0) return fail("invalid solver_index");  // JniCaffeNet.cpp:259-262
     std::string err;
-    if (!N(net)->init(solver_index, enable_nn != 0, &err)) return fail(err);
+    CaffeNet* r = R(net, solver_index);
+    if (!r) return fail("invalid solver_index");
+    if (!r->init(0, enable_nn != 0, &err)) return fail(err);
     return 1;
   })
 }
@@ -189,7 +193,9 @@ int cos_net_train(cos_net* net, int solver_index, const cos_blob* data, int ndat
     if (solver_index < 0) return fail("invalid solver_index");
     if (!data) return fail("data is NULL");  // JniCaffeNet.cpp:391-395
     std::string err;
-    if (!N(net)->train(solver_index, data, ndata, &err)) return fail(err);
+    CaffeNet* r = R(net, solver_index);
+    if (!r) return fail("invalid solver_index");
+    if (!r->train(0, data, ndata, &err)) return fail(err);
     return 1;
   })
 }
@@ -212,19 +218,23 @@ int cos_net_get_validation_output_blobs(cos_net*, int, cos_blob*) {
 
 int cos_net_device_id(cos_net* net, int solver_index) {
   if (!net || solver_index < 0) return fail("invalid solver_index", -1);  // JniCaffeNet.cpp:238-241
-  return N(net)->deviceID(solver_index);
+  CaffeNet* r = R(net, solver_index);
+  return r ? r->deviceID(0) : fail("invalid solver_index", -1);
 }
 int cos_net_get_init_iter(cos_net* net, int solver_index) {
   if (!net || solver_index < 0) return fail("invalid solver_index", -1);
-  return N(net)->getInitIter(solver_index);
+  CaffeNet* r = R(net, solver_index);
+  return r ? r->getInitIter(0) : fail("invalid solver_index", -1);
 }
 int cos_net_get_max_iter(cos_net* net, int solver_index) {
   if (!net || solver_index < 0) return fail("invalid solver_index", -1);
-  return N(net)->getMaxIter(solver_index);
+  CaffeNet* r = R(net, solver_index);
+  return r ? r->getMaxIter(0) : fail("invalid solver_index", -1);
 }
 int cos_net_get_test_iter(cos_net* net, int solver_index) {
   if (!net || solver_index < 0) return fail("invalid solver_index", -1);
-  return N(net)->getTestIter(solver_index);
+  CaffeNet* r = R(net, solver_index);
+  return r ? r->getTestIter(0) : fail("invalid solver_index", -1);
 }
 int cos_net_get_test_interval(cos_net* net) {
   if (!net) return fail("net is NULL", -1);
@@ -247,12 +257,19 @@ int cos_net_set_forward_backward(cos_net* net, cos_forward_backward_fn fn, void*
   return 1;
 }
 
-float* cos_net_data(cos_net* net, int solver_index) { return (net && solver_index == 0) ? N(net)->data() : nullptr; }
-float* cos_net_diff(cos_net* net, int solver_index) { return (net && solver_index == 0) ? N(net)->diff() : nullptr; }
-float* cos_net_history(cos_net* net, int solver_index) {
-  return (net && solver_index == 0) ? N(net)->history() : nullptr;
+float* cos_net_data(cos_net* net, int solver_index) {
+  CaffeNet* r = R(net, solver_index);
+  return r ? r->data() : nullptr;
 }
-int64_t cos_net_param_count(cos_net* net) { return net ? static_cast<int64_t>(N(net)->param_count()) : -1; }
+float* cos_net_diff(cos_net* net, int solver_index) {
+  CaffeNet* r = R(net, solver_index);
+  return r ? r->diff() : nullptr;
+}
+float* cos_net_history(cos_net* net, int solver_index) {
+  CaffeNet* r = R(net, solver_index);
+  return r ? r->history() : nullptr;
+}
+int64_t cos_net_param_count(cos_net* net) { return net ? static_cast<int64_t>(R(net, 0)->param_count()) : -1; }
 
 int cos_net_shard(cos_net* net, int rank, uint64_t* offs, uint64_t* size) {
   if (!net || !offs || !size) return fail("bad argument");
@@ -262,16 +279,18 @@ int cos_net_shard(cos_net* net, int rank, uint64_t* offs, uint64_t* size) {
   return 1;
 }
 
-int cos_net_iter(cos_net* net) { return net ? N(net)->iter() : -1; }
-float cos_net_learning_rate(cos_net* net) { return net ? N(net)->current_rate() : 0.f; }
-float cos_net_last_loss(cos_net* net) { return net ? N(net)->last_loss() : 0.f; }
+int cos_net_iter(cos_net* net) { return net ? R(net, 0)->iter() : -1; }
+float cos_net_learning_rate(cos_net* net) { return net ? R(net, 0)->current_rate() : 0.f; }
+float cos_net_last_loss(cos_net* net) { return net ? R(net, 0)->last_loss() : 0.f; }
 
 int cos_net_sync_step(cos_net* net, int solver_index, void* cuda_stream) {
   COS_GUARD(0, {
     if (!net) return fail("net is NULL");
     if (solver_index < 0) return fail("invalid solver_index");
     std::string err;
-    if (!N(net)->sync_step(solver_index, static_cast<cudaStream_t>(cuda_stream), cuda_stream == nullptr, &err))
+    CaffeNet* r = R(net, solver_index);
+    if (!r) return fail("invalid solver_index");
+    if (!r->sync_step(0, static_cast<cudaStream_t>(cuda_stream), cuda_stream == nullptr, &err))
       return fail(err);
     return 1;
   })
@@ -282,7 +301,9 @@ int cos_net_all_gather_weights(cos_net* net, int solver_index, void* cuda_stream
     if (!net) return fail("net is NULL");
     if (solver_index < 0) return fail("invalid solver_index");
     std::string err;
-    if (!N(net)->all_gather_weights(static_cast<cudaStream_t>(cuda_stream), cuda_stream == nullptr, &err))
+    CaffeNet* r = R(net, solver_index);
+    if (!r) return fail("invalid solver_index");
+    if (!r->all_gather_weights(static_cast<cudaStream_t>(cuda_stream), cuda_stream == nullptr, &err))
       return fail(err);
     return 1;
   })
@@ -307,7 +328,7 @@ int64_t cos_net_get_option(cos_net* net, const char* name) {
   if (!net || !name) return -1;
   return N(net)->get_option(name);
 }
-float cos_net_last_kernel_ms(cos_net* net) { return net ? N(net)->last_kernel_ms() : -1.f; }
+float cos_net_last_kernel_ms(cos_net* net) { return net ? R(net, 0)->last_kernel_ms() : -1.f; }
 int64_t cos_net_launch_count(cos_net* net) { return net ? N(net)->launch_count() : 0; }
 
 // ------------------------------------------------------------- adapter API

@@ -145,3 +145,53 @@ def test_full_size_caffenet_properties(cos, oracle, kernel):
         assert_bits_equal(R.weights(0), w0, "idempotence under zero gradient")
     finally:
         R.close()
+
+
+def test_snapshot_restore_resumes_bit_exactly(cos, oracle, tmp_path):
+    """Checkpoint/resume (CaffeNet.cpp:196-205 restore path, CaffeProcessor.scala:454-465 snapshot):
+    snapshot at iteration 2, resume in a NEW net from the files, and the continued run must equal the
+    uninterrupted one bit for bit (weights, history, iteration counter, learning-rate schedule)."""
+    from caffeonspark_b200 import nets
+    from gpu_util import to_dev, to_host
+    import torch
+    (tmp_path / "net.prototxt").write_text(nets.net_prototxt("cifar10_quick"))
+    prefix = str(tmp_path / "ckpt")
+    (tmp_path / "solver.prototxt").write_text(
+        f'net: "net.prototxt"\nbase_lr: 0.01\nmomentum: 0.9\nweight_decay: 0.004\nlr_policy: "inv"\n'
+        f'gamma: 0.01\npower: 0.75\nmax_iter: 100\nsnapshot_prefix: "{prefix}"\n')
+    solver = str(tmp_path / "solver.prototxt")
+    P = nets.EXPECTED_PARAM_COUNT["cifar10_quick"]
+    grads = [oracle.fill(P, 21, 4096 * (t + 1), 0.01) for t in range(4)]
+
+    def run_steps(net, ts):
+        for t in ts:
+            to_dev(net.diff(), grads[t])
+            torch.cuda.synchronize()
+            assert net.sync_step(0) and net.synchronize(), net.last_error()
+
+    a = cos.CaffeNet(solver)
+    try:
+        assert a.connect(a.localAddresses())
+        to_dev(a.data(), oracle.fill(P, 21, 0, 0.05))
+        run_steps(a, [0, 1])
+        it = a.snapshot()
+        assert it == 2
+        model, state = a.snapshotFilename(it, False), a.snapshotFilename(it, True)
+        rate_at_2 = a.learning_rate()
+        run_steps(a, [2, 3])
+        w_ref, h_ref = to_host(a.data()), to_host(a.history())
+    finally:
+        a.deallocate()
+    b = cos.CaffeNet(solver, model, state)
+    try:
+        assert b.connect(b.localAddresses())
+        assert b.getInitIter(0) == 2 and b.iter() == 2
+        assert np.float32(b.learning_rate()).tobytes() == np.float32(rate_at_2).tobytes()
+        run_steps(b, [2, 3])
+        assert b.iter() == 4
+        assert_bits_equal(to_host(b.data()), w_ref, "weights after resume")
+        assert_bits_equal(to_host(b.history()), h_ref, "history after resume")
+    finally:
+        b.deallocate()
+    with pytest.raises(cos.CosError, match="not a matching snapshot"):
+        cos.CaffeNet(solver, state, model)  # swapped files must be rejected

@@ -155,3 +155,67 @@ def test_snapshot_gathers_sharded_history(cos, oracle, tmp_path):
         assert_bits_equal(rawm[-4 * sim.P:].view(np.float32), sim.consistent_weights(), "snapshot weights")
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("executors,k", [(1, 2), (2, 2), (1, 3)])
+def test_multi_device_executor(cos, oracle, executors, k, monkeypatch):
+    """`-devices k`: one CaffeNet handle with k local solvers; every local GPU is a rank of one
+    collective of executors*k ranks (rank = node_rank*k + solver_index).  The oracle for this mode is the flat
+    reference order over all executors*k ranks (the reference itself sums a local GPU tree first,
+    parallel.cpp:325-380, so it agrees with this to rounding, not bitwise).  With fewer than k GPUs the local
+    solvers share the last device (COS_ALLOW_SHARED_DEVICE, tests only)."""
+    import concurrent.futures as cf
+    import torch
+    from gpu_util import to_dev, to_host
+    monkeypatch.setenv("COS_ALLOW_SHARED_DEVICE", "1")
+    world = executors * k
+    counts, lm, dm = [1001, 13, 640, 10], [1, 2, 1, 2], [1, 0, 1, 1]
+    desc = cos.SolverDesc(counts, lm, dm, **HP)
+    sim = oracle.Simulation(world, counts, lm, dm, seed=91, **HP)
+    nets = [cos.CaffeNet(desc, "", "", k, executors, e, True, cos.CaffeNet.SOCKET, -1, 0) for e in range(executors)]
+    try:
+        for n in nets:
+            n.set_option("grid", 4)
+            n.set_option("block", 128)
+            n.set_option("barrier_timeout_ms", 8000)
+            n.set_option("initial_gather", 0)
+            assert [n.deviceID(i) for i in range(k)] == [min(i, torch.cuda.device_count() - 1) for i in range(k)]
+            assert n.deviceID(k) == -1 and n.init(k) is False
+            for i in range(k):
+                to_dev(n.data(i), sim.data[n.global_rank(i)])
+        torch.cuda.synchronize()
+        table = [n.localAddresses() for n in nets]
+        assert all(len(t) == executors for t in table)
+        with cf.ThreadPoolExecutor(executors) as ex:
+            oks = list(ex.map(lambda e: nets[e].connect([table[p][e] if p != e else "" for p in range(executors)]),
+                              range(executors)))
+        assert all(oks), [n.last_error() for n in nets]
+        for n in nets:
+            for i in range(k):
+                assert n.all_gather_weights(i), n.last_error()
+        for n in nets:
+            assert n.synchronize(), n.last_error()
+        with cf.ThreadPoolExecutor(executors) as ex:
+            assert all(ex.map(lambda n: n.sync(), nets))
+        for t in range(3):
+            grads = [oracle.fill(sim.P, 91, (t + 1) * 4096 + r, 0.01) for r in range(world)]
+            sim.step()
+            for n in nets:
+                for i in range(k):
+                    to_dev(n.diff(i), grads[n.global_rank(i)])
+            torch.cuda.synchronize()
+            for n in nets:
+                for i in range(k):
+                    assert n.sync_step(i), n.last_error()
+            for n in nets:
+                assert n.synchronize(), n.last_error()
+            cw, ch = sim.consistent_weights(), sim.consistent_history()
+            for n in nets:
+                for i in range(k):
+                    assert_bits_equal(to_host(n.data(i)), cw, f"weights iter {t} executor {n.node_rank} solver {i}")
+                    o, s = cos.chunk(sim.P, world, n.global_rank(i))
+                    assert_bits_equal(to_host(n.history(i))[o:o + s], ch[o:o + s], f"history iter {t}")
+        assert nets[0].iter() == 3
+    finally:
+        with cf.ThreadPoolExecutor(executors) as ex:
+            list(ex.map(lambda n: n.deallocate(), nets))
