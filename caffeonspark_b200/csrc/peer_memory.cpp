@@ -27,6 +27,7 @@ struct DriverApi {
   CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
   CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
   CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*MemGetAccess)(unsigned long long*, const CUmemLocation*, CUdeviceptr) = nullptr;
   CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType,
                                          unsigned long long) = nullptr;
   CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*,
@@ -76,6 +77,7 @@ const DriverApi& driver() {
     if (ok) {
       // optional (NVLS); absence just disables multicast
       std::string ignore;
+      resolve("cuMemGetAccess", &api.MemGetAccess, &ignore);
       resolve("cuMulticastCreate", &api.MulticastCreate, &ignore);
       resolve("cuMulticastAddDevice", &api.MulticastAddDevice, &ignore);
       resolve("cuMulticastBindMem", &api.MulticastBindMem, &ignore);
@@ -113,7 +115,21 @@ CUmemAllocationProp device_prop(int device) {
   return prop;
 }
 
+// Several in-process ranks on the same GPU may ask for access to the same arena at the same time:
+// serialise, and skip the call when the device can already read and write the range.
+std::mutex g_access_mu;
+
 bool set_rw(CUdeviceptr va, size_t bytes, int device, std::string* err) {
+  std::lock_guard<std::mutex> g(g_access_mu);
+  if (driver().MemGetAccess) {
+    CUmemLocation loc;
+    memset(&loc, 0, sizeof(loc));
+    loc.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    loc.id = device;
+    unsigned long long flags = 0;
+    if (driver().MemGetAccess(&flags, &loc, va) == CUDA_SUCCESS && flags == CU_MEM_ACCESS_FLAGS_PROT_READWRITE)
+      return true;
+  }
   CUmemAccessDesc acc;
   memset(&acc, 0, sizeof(acc));
   acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;

@@ -186,10 +186,13 @@ def test_multi_device_executor(cos, oracle, executors, k, monkeypatch):
         torch.cuda.synchronize()
         table = [n.localAddresses() for n in nets]
         assert all(len(t) == executors for t in table)
+        def conn(e):  # cos_last_error() is thread-local: read it on the thread that made the call
+            ok = nets[e].connect([table[p][e] if p != e else "" for p in range(executors)])
+            return ok, nets[e].last_error()
+
         with cf.ThreadPoolExecutor(executors) as ex:
-            oks = list(ex.map(lambda e: nets[e].connect([table[p][e] if p != e else "" for p in range(executors)]),
-                              range(executors)))
-        assert all(oks), [n.last_error() for n in nets]
+            oks = list(ex.map(conn, range(executors)))
+        assert all(ok for ok, _ in oks), oks
         for n in nets:
             for i in range(k):
                 assert n.all_gather_weights(i), n.last_error()
