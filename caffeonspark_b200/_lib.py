@@ -62,6 +62,11 @@ SYMBOLS = [
     ("cos_net_get_test_iter", _i, [_vp, _i]),
     ("cos_net_get_test_interval", _i, [_vp]),
     ("cos_net_snapshot", _i, [_vp]),
+    ("cos_net_snapshot_filename", _i, [_vp, _i, _i, _cp, _i]),
+    ("cos_caffemodel_write", _i, [_cp, _cp, _i, _pcp, _pcp, _c.POINTER(_i), _c.POINTER(_i64), _c.POINTER(_vp)]),
+    ("cos_caffemodel_read", _i64, [_cp, _cp, _i, _vp, _i64]),
+    ("cos_solverstate_write", _i, [_cp, _i, _i, _cp, _i, _c.POINTER(_i), _c.POINTER(_i64), _c.POINTER(_vp)]),
+    ("cos_solverstate_read", _i64, [_cp, _c.POINTER(_i), _c.POINTER(_i), _cp, _i, _i, _vp, _i64]),
     ("cos_net_get_validation_output_blob_names", _i, [_vp, _c.POINTER(_pcp)]),
     ("cos_net_get_validation_output_blobs", _i, [_vp, _i, _c.POINTER(cos_blob)]),
     ("cos_net_set_forward_backward", _i, [_vp, FORWARD_BACKWARD_FN, _vp]),

@@ -100,6 +100,36 @@ def parse_solver(solver_conf_file):
                       test_interval=d.test_interval, snapshot_prefix=pre.value.decode(), batch_size=bs.value)
 
 
+def read_caffemodel_blob(path, layer_name, blob_index=0):
+    """One blob of a Caffe .caffemodel (ours or stock Caffe's) as a flat float32 numpy array."""
+    import numpy as np
+    L = _lib.lib()
+    n = L.cos_caffemodel_read(str(path).encode(), layer_name.encode(), blob_index, None, 0)
+    if n < 0:
+        raise CosError(_err())
+    out = np.empty(n, np.float32)
+    L.cos_caffemodel_read(str(path).encode(), layer_name.encode(), blob_index, out.ctypes.data, n)
+    return out
+
+
+def read_solverstate(path):
+    """-> (iter, current_step, learned_net, [history blobs as flat float32 arrays]) of a Caffe .solverstate."""
+    import numpy as np
+    L = _lib.lib()
+    it, step = ctypes.c_int(), ctypes.c_int()
+    buf = ctypes.create_string_buffer(4096)
+    n = L.cos_solverstate_read(str(path).encode(), ctypes.byref(it), ctypes.byref(step), buf, 4096, -1, None, 0)
+    if n < 0:
+        raise CosError(_err())
+    hist = []
+    for k in range(n):
+        m = L.cos_solverstate_read(str(path).encode(), None, None, None, 0, k, None, 0)
+        a = np.empty(m, np.float32)
+        L.cos_solverstate_read(str(path).encode(), None, None, None, 0, k, a.ctypes.data, m)
+        hist.append(a)
+    return it.value, step.value, buf.value.decode(), hist
+
+
 class _DevArray:
     """__cuda_array_interface__ view of a raw device pointer (zero-copy)."""
 
@@ -221,11 +251,13 @@ class CaffeNet:
         return self._L.cos_net_snapshot(self._h)
 
     def snapshotFilename(self, it, isState):
-        """CaffeNet.java:192-207 (this library writes .cosstate / .cosmodel)."""
+        """CaffeNet.java:192-207: <snapshot_prefix>_iter_<it>.solverstate / .caffemodel (+ ".h5")."""
         if it < 0:
             return None
-        prefix = self.desc.snapshot_prefix or "cos_b200"
-        return f"{prefix}_iter_{it}" + (".cosstate" if isState else ".cosmodel")
+        buf = ctypes.create_string_buffer(4096)
+        if not self._L.cos_net_snapshot_filename(self._h, it, int(bool(isState)), buf, 4096):
+            return None
+        return buf.value.decode()
 
     # ---- hot-path surface (what a native gradient producer uses)
     def last_error(self):

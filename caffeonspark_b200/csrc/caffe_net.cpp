@@ -1,6 +1,8 @@
 // caffe_net.cpp -- see caffe_net.hpp.
 #include "caffe_net.hpp"
 
+#include "caffe_proto_io.hpp"
+
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -463,29 +465,37 @@ int64_t CaffeNet::get_option(const std::string& name) const {
 }
 
 // ---------------------------------------------------------------- snapshot
-// Flat little-endian files: header {magic, version, iter, current_step, count,
-// nblobs, counts[nblobs]} + fp32 payload.  Rank 0 is the only caller in the
-// reference (CaffeProcessor.scala:454-465); its weights are globally
-// consistent here (the kernel all-gathers every step), and the history of the
-// other shards is read straight from the owners' arenas over NVLink, which
-// removes the reference's stale-shard quirks.
-namespace {
-bool write_flat(const std::string& path, const char* magic, int iter, int current_step, const SolverSpec& spec,
-                uint64_t count, const std::vector<float>& payload, std::string* err) {
-  FILE* f = fopen(path.c_str(), "wb");
-  if (!f) {
-    *err = "cannot open '" + path + "' for writing";
-    return false;
-  }
-  int32_t hdr[4] = {1, iter, current_step, static_cast<int32_t>(spec.counts.size())};
-  bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(&count, 8, 1, f) == 1;
-  for (int64_t c : spec.counts) ok = ok && fwrite(&c, 8, 1, f) == 1;
-  ok = ok && fwrite(payload.data(), sizeof(float), payload.size(), f) == payload.size();
-  ok = (fclose(f) == 0) && ok;
-  if (!ok) *err = "short write to '" + path + "'";
-  return ok;
+// Stock-Caffe binaryproto files (caffe_proto_io.cpp): <prefix>_iter_<n>.caffemodel = NetParameter with one
+// LayerParameter per parameterised layer, <prefix>_iter_<n>.solverstate = SolverState {iter, learned_net,
+// history[], current_step} -- the names Solver::SnapshotFilename (solver.cpp:446-449) and
+// CaffeNet.java:192-207 produce, so FSUtils.GenModelOrState finds them.  Rank 0 is the only caller in the
+// reference (CaffeProcessor.scala:454-465); its weights are globally consistent here (the kernel
+// all-gathers every step), and the history of the other shards is read straight from the owners' arenas
+// over NVLink, which removes the reference's stale-shard quirks.
+std::string CaffeNet::snapshot_filename(int iter, bool is_state) const {
+  const std::string prefix = spec_.snapshot_prefix.empty() ? std::string("cos_b200") : spec_.snapshot_prefix;
+  // snapshot_format HDF5 only changes the NAME (CaffeNet.java:203-205 appends ".h5"); the content stays
+  // binaryproto -- there is no HDF5 writer here and restore() goes by content.
+  return prefix + "_iter_" + std::to_string(iter) + (is_state ? ".solverstate" : ".caffemodel") +
+         (spec_.snapshot_hdf5 ? ".h5" : "");
 }
-}  // namespace
+
+std::vector<BlobView> CaffeNet::blob_views(const float* flat) const {
+  std::vector<BlobView> v;
+  uint64_t off = 0;
+  for (size_t k = 0; k < spec_.counts.size(); ++k) {
+    BlobView b;
+    b.layer_name = k < spec_.layer_names.size() ? spec_.layer_names[k] : "blob" + std::to_string(k);
+    b.layer_type = k < spec_.layer_types.size() ? spec_.layer_types[k] : "Blob";
+    if (k < spec_.shapes.size()) b.shape = spec_.shapes[k];
+    else b.shape.assign(1, spec_.counts[k]);
+    b.count = static_cast<uint64_t>(spec_.counts[k]);
+    b.data = flat + off;
+    off += b.count;
+    v.push_back(std::move(b));
+  }
+  return v;
+}
 
 int CaffeNet::snapshot(std::string* err) {
   std::lock_guard<std::mutex> g(mu_);
@@ -513,50 +523,75 @@ int CaffeNet::snapshot(std::string* err) {
     *err = rt_err("snapshot: copy to host", e);
     return -1;
   }
-  const std::string prefix = spec_.snapshot_prefix.empty() ? std::string("cos_b200") : spec_.snapshot_prefix;
-  const std::string stem = prefix + "_iter_" + std::to_string(iter_);
-  if (!write_flat(stem + ".cosmodel", "COSB2MDL", iter_, current_step_, spec_, count_, w, err)) return -1;
-  if (!write_flat(stem + ".cosstate", "COSB2STA", iter_, current_step_, spec_, count_, h, err)) return -1;
+  const std::string model = snapshot_filename(iter_, false), state = snapshot_filename(iter_, true);
+  if (!write_caffemodel(model, spec_.net_name, blob_views(w.data()), err)) return -1;
+  if (!write_solverstate(state, iter_, current_step_, model, blob_views(h.data()), err)) return -1;
   return iter_;
 }
 
+// CaffeNet.cpp:196-205: state + model -> weights from the model file, history / iter / current_step from the
+// state (Solver::Restore); model only -> copyLayers (weights by layer NAME, Net::CopyTrainedLayersFrom).
 bool CaffeNet::restore(const std::string& model_file, const std::string& state_file, std::string* err) {
-  auto read_flat = [&](const std::string& path, const char* magic, std::vector<float>* out, int* iter,
-                       int* step) -> bool {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) {
-      *err = "cannot open '" + path + "'";
+  COS_RT(cudaSetDevice(device_));
+  std::string model = model_file;
+  if (!state_file.empty()) {
+    int it = 0, step = 0;
+    std::string learned;
+    std::vector<ParsedBlob> hist;
+    if (!read_solverstate(state_file, &it, &step, &learned, &hist, err)) return false;
+    if (hist.size() != spec_.counts.size()) {
+      *err = "'" + state_file + "' is not a matching snapshot of this net: " + std::to_string(hist.size()) +
+             " history blobs, the net has " + std::to_string(spec_.counts.size()) + " learnable blobs";
       return false;
     }
-    char m[8];
-    int32_t hdr[4];
-    uint64_t count = 0;
-    bool ok = fread(m, 1, 8, f) == 8 && memcmp(m, magic, 8) == 0 && fread(hdr, sizeof(hdr), 1, f) == 1 &&
-              fread(&count, 8, 1, f) == 1 && hdr[0] == 1 && count == count_;
-    if (ok) ok = fseek(f, static_cast<long>(hdr[3]) * 8, SEEK_CUR) == 0;
-    if (ok) {
-      out->resize(count);
-      ok = fread(out->data(), sizeof(float), count, f) == count;
-      *iter = hdr[1];
-      *step = hdr[2];
+    std::vector<float> flat(count_, 0.f);
+    uint64_t off = 0;
+    for (size_t k = 0; k < hist.size(); ++k) {
+      if (hist[k].data.size() != static_cast<size_t>(spec_.counts[k])) {
+        *err = "'" + state_file + "' is not a matching snapshot of this net: history blob " + std::to_string(k) +
+               " has " + std::to_string(hist[k].data.size()) + " elements, expected " +
+               std::to_string(spec_.counts[k]);
+        return false;
+      }
+      memcpy(flat.data() + off, hist[k].data.data(), hist[k].data.size() * sizeof(float));
+      off += hist[k].data.size();
     }
-    fclose(f);
-    if (!ok) *err = "'" + path + "' is not a matching snapshot of this net";
-    return ok;
-  };
-  COS_RT(cudaSetDevice(device_));
-  int it = 0, st = 0;
-  std::vector<float> buf;
-  if (!model_file.empty()) {
-    if (!read_flat(model_file, "COSB2MDL", &buf, &it, &st)) return false;
-    COS_RT(cudaMemcpy(data_, buf.data(), count_ * sizeof(float), cudaMemcpyHostToDevice));
-  }
-  if (!state_file.empty()) {  // CaffeNet.cpp:198-203: Restore() also resumes iter_
-    if (!read_flat(state_file, "COSB2STA", &buf, &it, &st)) return false;
-    COS_RT(cudaMemcpy(hist_, buf.data(), count_ * sizeof(float), cudaMemcpyHostToDevice));
+    COS_RT(cudaMemcpy(hist_, flat.data(), count_ * sizeof(float), cudaMemcpyHostToDevice));
     iter_ = it;
-    current_step_ = st;
+    current_step_ = step;
     spec_.init_iter = it;
+    if (model.empty()) model = learned;  // Solver::Restore follows state.learned_net()
+  }
+  if (!model.empty()) {
+    std::vector<ParsedLayer> layers;
+    std::string name;
+    if (!read_caffemodel(model, &name, &layers, err)) return false;
+    std::vector<float> flat(count_);
+    COS_RT(cudaMemcpy(flat.data(), data_, count_ * sizeof(float), cudaMemcpyDeviceToHost));
+    uint64_t off = 0;
+    int matched = 0;
+    for (size_t k = 0; k < spec_.counts.size(); ++k) {
+      const std::string& lname = k < spec_.layer_names.size() ? spec_.layer_names[k] : std::string();
+      size_t j = 0;  // index of blob k inside its layer
+      for (size_t q = k; q > 0 && q - 1 < spec_.layer_names.size() && spec_.layer_names[q - 1] == lname; --q) ++j;
+      for (const ParsedLayer& L : layers) {
+        if (L.name != lname) continue;
+        if (j >= L.blobs.size() || L.blobs[j].data.size() != static_cast<size_t>(spec_.counts[k])) {
+          *err = "'" + model + "' is not a matching snapshot of this net: layer '" + lname + "' blob " +
+                 std::to_string(j) + " does not have " + std::to_string(spec_.counts[k]) + " elements";
+          return false;  // CopyTrainedLayersFrom CHECKs the shapes (net.cpp)
+        }
+        memcpy(flat.data() + off, L.blobs[j].data.data(), L.blobs[j].data.size() * sizeof(float));
+        ++matched;
+        break;
+      }
+      off += static_cast<uint64_t>(spec_.counts[k]);
+    }
+    if (matched == 0 && !spec_.counts.empty()) {
+      *err = "'" + model + "' is not a matching snapshot of this net: no layer name matches";
+      return false;
+    }
+    COS_RT(cudaMemcpy(data_, flat.data(), count_ * sizeof(float), cudaMemcpyHostToDevice));
   }
   return true;
 }

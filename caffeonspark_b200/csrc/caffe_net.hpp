@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/caffedistri_b200.h"
+#include "caffe_proto_io.hpp"
 #include "fused_sync_sgd.hpp"
 #include "peer_adapter.hpp"
 #include "peer_memory.hpp"
@@ -47,7 +48,9 @@ class CaffeNet {
   bool init(int solver_index, bool enable_nn, std::string* err);
   bool train(int solver_index, const cos_blob* data, int ndata, std::string* err);
   virtual int snapshot(std::string* err);
-  // resume from files written by snapshot() (CaffeNet.cpp:198-205 restore path)
+  std::string snapshot_filename(int iter, bool is_state) const;  // Solver::SnapshotFilename
+  std::vector<BlobView> blob_views(const float* flat) const;
+  // resume from snapshot files, ours or stock Caffe's (CaffeNet.cpp:198-205 restore path)
   bool restore(const std::string& model_file, const std::string& state_file, std::string* err);
   int getInitIter(int solver_index) const { return solver_index == 0 ? spec_.init_iter : -1; }
   int getMaxIter(int solver_index) const { return solver_index == 0 ? spec_.max_iter : -1; }

@@ -12,6 +12,7 @@
 
 #include "../../include/caffedistri_b200.h"
 #include "caffe_net.hpp"
+#include "caffe_proto_io.hpp"
 #include "peer_adapter.hpp"
 #include "solver_spec.hpp"
 
@@ -57,7 +58,11 @@ bool spec_from_desc(const cos_solver_desc* d, SolverSpec* s, std::string* err) {
     s->lr_mult.push_back(d->lr_mult ? d->lr_mult[k] : 1.0f);
     s->decay_mult.push_back(d->decay_mult ? d->decay_mult[k] : 1.0f);
     s->blob_names.push_back("blob." + std::to_string(k));
+    s->layer_names.push_back("blob" + std::to_string(k));  // no net definition: one pseudo layer per blob
+    s->layer_types.push_back("Blob");
+    s->shapes.push_back({d->counts[k]});
   }
+  s->net_name = "cos_net";
   s->lr_policy = d->lr_policy ? d->lr_policy : "fixed";
   s->base_lr = d->base_lr;
   s->gamma = d->gamma;
@@ -251,6 +256,14 @@ int cos_net_snapshot(cos_net* net) {
   })
 }
 
+int cos_net_snapshot_filename(cos_net* net, int iter, int is_state, char* buf, int cap) {
+  if (!net || !buf || cap <= 0 || iter < 0) return fail("bad argument");
+  const std::string s = R(net, 0)->snapshot_filename(iter, is_state != 0);
+  if (static_cast<int>(s.size()) >= cap) return fail("buffer too small");
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return 1;
+}
+
 int cos_net_set_forward_backward(cos_net* net, cos_forward_backward_fn fn, void* user) {
   if (!net) return fail("net is NULL");
   N(net)->set_forward_backward(fn, user);
@@ -385,6 +398,94 @@ int cos_adapter_fetch_fd(cos_adapter* a, int peer, const char* key, void* meta, 
     memcpy(meta, m.data(), m.size() < static_cast<size_t>(meta_cap) ? m.size() : meta_cap);
   }
   return fd;  // -1: metadata only
+}
+
+// ------------------------------------------------- snapshot file utilities
+namespace {
+std::vector<cosb::BlobView> views_from_c(int nblobs, const char* const* layer_names, const char* const* layer_types,
+                                         const int* shape_ndims, const int64_t* dims_flat,
+                                         const float* const* data) {
+  std::vector<cosb::BlobView> v(nblobs);
+  size_t d = 0;
+  for (int k = 0; k < nblobs; ++k) {
+    v[k].layer_name = layer_names ? layer_names[k] : "";
+    v[k].layer_type = layer_types ? layer_types[k] : "";
+    v[k].count = 1;
+    for (int i = 0; i < shape_ndims[k]; ++i) {
+      v[k].shape.push_back(dims_flat[d + i]);
+      v[k].count *= static_cast<uint64_t>(dims_flat[d + i]);
+    }
+    d += shape_ndims[k];
+    v[k].data = data[k];
+  }
+  return v;
+}
+}  // namespace
+
+int cos_caffemodel_write(const char* path, const char* net_name, int nblobs, const char* const* layer_names,
+                         const char* const* layer_types, const int* shape_ndims, const int64_t* dims_flat,
+                         const float* const* data) {
+  COS_GUARD(0, {
+    if (!path || nblobs < 0 || (nblobs && (!layer_names || !shape_ndims || !dims_flat || !data)))
+      return fail("bad argument");
+    std::string err;
+    if (!cosb::write_caffemodel(path, net_name ? net_name : "",
+                                views_from_c(nblobs, layer_names, layer_types, shape_ndims, dims_flat, data), &err))
+      return fail(err);
+    return 1;
+  })
+}
+
+int64_t cos_caffemodel_read(const char* path, const char* layer_name, int blob_index, float* out, int64_t cap) {
+  COS_GUARD(-1, {
+    if (!path || !layer_name || blob_index < 0) return fail("bad argument", -1);
+    std::vector<cosb::ParsedLayer> layers;
+    std::string name, err;
+    if (!cosb::read_caffemodel(path, &name, &layers, &err)) return fail(err, -1);
+    for (const auto& L : layers) {
+      if (L.name != layer_name) continue;
+      if (blob_index >= static_cast<int>(L.blobs.size())) return fail("layer has fewer blobs", -1);
+      const auto& b = L.blobs[blob_index];
+      const int64_t n = static_cast<int64_t>(b.data.size());
+      if (out && cap >= n) memcpy(out, b.data.data(), n * sizeof(float));
+      return n;
+    }
+    return fail(std::string("no layer named '") + layer_name + "'", -1);
+  })
+}
+
+int cos_solverstate_write(const char* path, int iter, int current_step, const char* learned_net, int nblobs,
+                          const int* shape_ndims, const int64_t* dims_flat, const float* const* data) {
+  COS_GUARD(0, {
+    if (!path || nblobs < 0 || (nblobs && (!shape_ndims || !dims_flat || !data))) return fail("bad argument");
+    std::string err;
+    if (!cosb::write_solverstate(path, iter, current_step, learned_net ? learned_net : "",
+                                 views_from_c(nblobs, nullptr, nullptr, shape_ndims, dims_flat, data), &err))
+      return fail(err);
+    return 1;
+  })
+}
+
+int64_t cos_solverstate_read(const char* path, int* iter, int* current_step, char* learned_net, int learned_cap,
+                             int blob_index, float* out, int64_t cap) {
+  COS_GUARD(-1, {
+    if (!path) return fail("bad argument", -1);
+    int it = 0, st = 0;
+    std::string learned, err;
+    std::vector<cosb::ParsedBlob> hist;
+    if (!cosb::read_solverstate(path, &it, &st, &learned, &hist, &err)) return fail(err, -1);
+    if (iter) *iter = it;
+    if (current_step) *current_step = st;
+    if (learned_net && learned_cap > 0) {
+      strncpy(learned_net, learned.c_str(), learned_cap - 1);
+      learned_net[learned_cap - 1] = 0;
+    }
+    if (blob_index < 0) return static_cast<int64_t>(hist.size());  // number of history blobs
+    if (blob_index >= static_cast<int>(hist.size())) return fail("no such history blob", -1);
+    const int64_t n = static_cast<int64_t>(hist[blob_index].data.size());
+    if (out && cap >= n) memcpy(out, hist[blob_index].data.data(), n * sizeof(float));
+    return n;
+  })
 }
 
 // ------------------------------------------------------------ host helpers

@@ -265,6 +265,10 @@ bool net_layout(const Node& net, SolverSpec* spec, std::string* err) {
   spec->lr_mult.clear();
   spec->decay_mult.clear();
   spec->blob_names.clear();
+  spec->layer_names.clear();
+  spec->layer_types.clear();
+  spec->shapes.clear();
+  spec->net_name = net.str("name");
   // legacy "input:" / "input_shape" / "input_dim" net-level inputs
   {
     auto inputs = net.all("input");
@@ -299,6 +303,7 @@ bool net_layout(const Node& net, SolverSpec* spec, std::string* err) {
       return true;
     };
     std::vector<long> param_counts;  // learnable blobs this layer owns, in order
+    std::vector<std::vector<int64_t>> param_shapes;
     if (type == "MemoryData") {
       const Node* p = L->first("memory_data_param");
       if (!p) { *err = "MemoryData layer without memory_data_param"; return false; }
@@ -350,16 +355,21 @@ bool net_layout(const Node& net, SolverSpec* spec, std::string* err) {
       out[0] = in[0];
       if (type == "Convolution") {
         param_counts.push_back(nout * (in[1] / group) * k.h * k.w);  // conv_layer / base_conv_layer.cpp weight shape
+        param_shapes.push_back({nout, in[1] / group, k.h, k.w});
         out[1] = nout;
         out[2] = (in[2] + 2 * pad.h - (dil.h * (k.h - 1) + 1)) / st.h + 1;
         out[3] = (in[3] + 2 * pad.w - (dil.w * (k.w - 1) + 1)) / st.w + 1;
       } else {
         param_counts.push_back(in[1] * (nout / group) * k.h * k.w);
+        param_shapes.push_back({in[1], nout / group, k.h, k.w});
         out[1] = nout;
         out[2] = st.h * (in[2] - 1) + (dil.h * (k.h - 1) + 1) - 2 * pad.h;
         out[3] = st.w * (in[3] - 1) + (dil.w * (k.w - 1) + 1) - 2 * pad.w;
       }
-      if (bias) param_counts.push_back(nout);
+      if (bias) {
+        param_counts.push_back(nout);
+        param_shapes.push_back({nout});
+      }
       if (!tops.empty()) blobs[tops[0]] = out;
     } else if (type == "Pooling") {
       const Node* p = L->first("pooling_param");
@@ -387,7 +397,11 @@ bool net_layout(const Node& net, SolverSpec* spec, std::string* err) {
       if (axis < 0) axis += static_cast<long>(in.size());
       if (nout <= 0 || axis < 0 || axis > static_cast<long>(in.size())) { *err = "layer '" + name + "': bad inner_product_param"; return false; }
       param_counts.push_back(nout * prod(in, static_cast<size_t>(axis)));
-      if (p->boolean("bias_term", true)) param_counts.push_back(nout);
+      param_shapes.push_back({nout, prod(in, static_cast<size_t>(axis))});  // inner_product_layer.cpp: N x K
+      if (p->boolean("bias_term", true)) {
+        param_counts.push_back(nout);
+        param_shapes.push_back({nout});
+      }
       Shape out(in.begin(), in.begin() + axis);
       out.push_back(nout);
       if (!tops.empty()) blobs[tops[0]] = out;
@@ -429,6 +443,9 @@ bool net_layout(const Node& net, SolverSpec* spec, std::string* err) {
       spec->lr_mult.push_back(i < pspecs.size() ? static_cast<float>(pspecs[i]->num("lr_mult", 1.0)) : 1.0f);
       spec->decay_mult.push_back(i < pspecs.size() ? static_cast<float>(pspecs[i]->num("decay_mult", 1.0)) : 1.0f);
       spec->blob_names.push_back(name + "." + std::to_string(i));
+      spec->layer_names.push_back(name);
+      spec->layer_types.push_back(type);
+      spec->shapes.push_back(param_shapes[i]);
     }
   }
   return true;
@@ -470,6 +487,7 @@ bool parse_solver_prototxt(const std::string& solver_path, SolverSpec* spec, std
   spec->iter_size = static_cast<int>(s.integer("iter_size", 1));
   spec->clip_gradients = static_cast<float>(s.num("clip_gradients", -1.0));
   spec->solver_mode_gpu = s.str("solver_mode", "GPU") != "CPU";
+  spec->snapshot_hdf5 = s.str("snapshot_format", "BINARYPROTO") == "HDF5";
   std::string type = s.str("type", "");
   if (type.empty()) {
     std::string st = s.str("solver_type", "SGD");  // deprecated enum field

@@ -20,7 +20,12 @@ struct SolverSpec {
   // learnable blobs in learnable_params() order
   std::vector<int64_t> counts;
   std::vector<float> lr_mult, decay_mult;
-  std::vector<std::string> blob_names;  // "<layer>.<index>" (diagnostics / snapshot)
+  std::vector<std::string> blob_names;  // "<layer>.<index>" (diagnostics)
+  // what Net::ToProto needs to write a stock-Caffe .caffemodel (solver.cpp:452-459)
+  std::string net_name;
+  std::vector<std::string> layer_names, layer_types;  // per learnable blob: owning layer
+  std::vector<std::vector<int64_t>> shapes;            // per learnable blob: Blob shape
+  bool snapshot_hdf5 = false;                          // SolverParameter.snapshot_format (caffe.proto:194-198)
   // SolverParameter
   std::string lr_policy = "fixed";
   float base_lr = 0.01f, gamma = 0.1f, power = 0.75f;

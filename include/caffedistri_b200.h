@@ -153,10 +153,15 @@ COS_API int cos_net_get_max_iter(cos_net* net, int solver_index);
 COS_API int cos_net_get_test_iter(cos_net* net, int solver_index);
 COS_API int cos_net_get_test_interval(cos_net* net);
 
-/* J:171 snapshot / JN:537-548, CN:735-738: writes <prefix>_iter_<n>.cosmodel /
- * .cosstate (flat fp32 weights / all-gathered history + layout header) and
- * returns the iteration, -1 on failure.  Collective when cluster_size > 1. */
+/* J:171 snapshot / JN:537-548, CN:735-738 -> Solver::Snapshot (solver.cpp:400-425):
+ * writes stock-Caffe binaryproto files <prefix>_iter_<n>.caffemodel (NetParameter)
+ * and .solverstate (SolverState; ".h5" appended to the NAMES for snapshot_format
+ * HDF5) and returns the iteration, -1 on failure.  Called on rank 0 only, like
+ * the reference (CaffeProcessor.scala:454-465); NOT collective: the history
+ * shards of the other ranks are read through their mapped arenas. */
 COS_API int cos_net_snapshot(cos_net* net);
+/* The path snapshot() writes for `iter` (== CaffeNet.java:192-207 snapshotFilename). 1/0. */
+COS_API int cos_net_snapshot_filename(cos_net* net, int iter, int is_state, char* buf, int cap);
 
 /* J:177,185 getValidationOutputBlobNames / getValidationOutputBlobs
  * (JN:587-673): no validation net here; return -1 with an error string. */
@@ -233,6 +238,22 @@ COS_API int cos_adapter_barrier(cos_adapter* a, int timeout_ms);
 COS_API int cos_adapter_offer_fd(cos_adapter* a, const char* key, int fd, const void* meta, int meta_len);
 COS_API int cos_adapter_fetch_fd(cos_adapter* a, int peer, const char* key, void* meta, int meta_cap,
                                  int timeout_ms);
+
+/* ---------------- snapshot file utilities (host only, Caffe binaryproto) ------ */
+/* Write / read the subset of caffe.proto the snapshots use (NetParameter.layer[].blobs[],
+ * SolverState) without libprotobuf.  Blob k has shape_ndims[k] dims taken in order from
+ * dims_flat; consecutive blobs with the same layer name form one layer.  Readers return
+ * the element count of the requested blob (copied into `out` when cap allows) or -1. */
+COS_API int cos_caffemodel_write(const char* path, const char* net_name, int nblobs, const char* const* layer_names,
+                                 const char* const* layer_types, const int* shape_ndims, const int64_t* dims_flat,
+                                 const float* const* data);
+COS_API int64_t cos_caffemodel_read(const char* path, const char* layer_name, int blob_index, float* out,
+                                    int64_t cap);
+COS_API int cos_solverstate_write(const char* path, int iter, int current_step, const char* learned_net, int nblobs,
+                                  const int* shape_ndims, const int64_t* dims_flat, const float* const* data);
+/* blob_index < 0: returns the number of history blobs. */
+COS_API int64_t cos_solverstate_read(const char* path, int* iter, int* current_step, char* learned_net,
+                                     int learned_cap, int blob_index, float* out, int64_t cap);
 
 /* -------------------------- host helpers (pure functions, no device) ------ */
 COS_API void cos_chunk(uint64_t param_count, int cluster_size, int peer, uint64_t* offs, uint64_t* size);

@@ -178,6 +178,7 @@ def test_snapshot_restore_resumes_bit_exactly(cos, oracle, tmp_path):
         assert it == 2
         model, state = a.snapshotFilename(it, False), a.snapshotFilename(it, True)
         rate_at_2 = a.learning_rate()
+        w_at_2 = to_host(a.data())
         run_steps(a, [2, 3])
         w_ref, h_ref = to_host(a.data()), to_host(a.history())
     finally:
@@ -193,5 +194,15 @@ def test_snapshot_restore_resumes_bit_exactly(cos, oracle, tmp_path):
         assert_bits_equal(to_host(b.history()), h_ref, "history after resume")
     finally:
         b.deallocate()
-    with pytest.raises(cos.CosError, match="not a matching snapshot"):
+    assert model.endswith("ckpt_iter_2.caffemodel") and state.endswith("ckpt_iter_2.solverstate")
+    # layer-wise content, readable by stock Caffe: conv1 weights are [32, 3, 5, 5]
+    assert cos.read_caffemodel_blob(model, "conv1", 0).size == 2400
+    assert cos.read_solverstate(state)[0] == 2
+    with pytest.raises(cos.CosError, match="not a SolverState"):
         cos.CaffeNet(solver, state, model)  # swapped files must be rejected
+    c = cos.CaffeNet(solver, model, "")     # weights only (copyLayers), iteration restarts at 0
+    try:
+        assert c.getInitIter(0) == 0
+        assert_bits_equal(to_host(c.data()), w_at_2, "copyLayers restores the weights")
+    finally:
+        c.deallocate()

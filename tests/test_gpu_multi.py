@@ -148,11 +148,13 @@ def test_snapshot_gathers_sharded_history(cos, oracle, tmp_path):
     try:
         it = R.nets[0].snapshot()              # rank 0 only, as CaffeProcessor does
         assert it == 2
-        raw = np.fromfile(R.nets[0].snapshotFilename(it, True), dtype=np.uint8)
-        hist = raw[-4 * sim.P:].view(np.float32)
-        assert_bits_equal(hist, sim.consistent_history(), "snapshot history = owners' shards")
-        rawm = np.fromfile(R.nets[0].snapshotFilename(it, False), dtype=np.uint8)
-        assert_bits_equal(rawm[-4 * sim.P:].view(np.float32), sim.consistent_weights(), "snapshot weights")
+        state_file, model_file = R.nets[0].snapshotFilename(it, True), R.nets[0].snapshotFilename(it, False)
+        assert state_file.endswith("_iter_2.solverstate") and model_file.endswith("_iter_2.caffemodel")
+        s_iter, s_step, learned, hist = cos.read_solverstate(state_file)   # stock-Caffe SolverState
+        assert (s_iter, learned) == (2, model_file) and [h.size for h in hist] == counts
+        assert_bits_equal(np.concatenate(hist), sim.consistent_history(), "snapshot history = owners' shards")
+        w = np.concatenate([cos.read_caffemodel_blob(model_file, f"blob{k}") for k in range(len(counts))])
+        assert_bits_equal(w, sim.consistent_weights(), "snapshot weights")
     finally:
         R.close()
 
