@@ -27,9 +27,17 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 prints exactly ONE JSON line on stdout: keep NCCL's version banner off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# Rank 0 prints exactly ONE JSON line on stdout.  Native libraries write to file descriptor 1 behind
+# Python's back (NCCL prints its "NCCL version ..." banner there at every debug level >= VERSION), so the
+# real stdout is set aside and fd 1 points at stderr for the whole run; emit() writes the line to the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 NVLINK_MEASURED_GBS = 770.0  # B200_PROFILING.md: measured peer copy per direction (900 nominal)
 HBM_FALLBACK_GBS = 6650.0    # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
@@ -354,7 +362,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
 
 
 def kernel_rooflines(C, nets, peaks, world, kernel=-1):
@@ -483,7 +491,7 @@ def run_reference(args):
            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample")},
            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def run_sweep(args):
@@ -599,7 +607,7 @@ def run_sweep(args):
             if world > 1:
                 dist.barrier()
     if rank == 0:
-        print(json.dumps({"sweep": rows, "n_gpus": world, "unit": "ms / GB/s", "steps": args.steps}))
+        emit({"sweep": rows, "n_gpus": world, "unit": "ms / GB/s", "steps": args.steps})
     if world > 1:
         dist.destroy_process_group()
 
