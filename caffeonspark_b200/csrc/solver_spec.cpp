@@ -350,7 +350,11 @@ bool net_layout(const Node& net, SolverSpec* spec, std::string* err) {
       HW pad = pair_field(*p, "pad", "pad_h", "pad_w", 0);
       HW dil = pair_field(*p, "dilation", "dilation_h", "dilation_w", 1);
       bool bias = p->boolean("bias_term", true);
-      if (nout <= 0 || k.h <= 0 || k.w <= 0 || group <= 0 || in[1] % group) { *err = "layer '" + name + "': bad convolution_param"; return false; }
+      if (nout <= 0 || k.h <= 0 || k.w <= 0 || group <= 0 || in[1] % group || nout % group || st.h <= 0 || st.w <= 0 ||
+          dil.h <= 0 || dil.w <= 0 || pad.h < 0 || pad.w < 0) {
+        *err = "layer '" + name + "': bad convolution_param";
+        return false;
+      }
       Shape out(4);
       out[0] = in[0];
       if (type == "Convolution") {
@@ -379,7 +383,10 @@ bool net_layout(const Node& net, SolverSpec* spec, std::string* err) {
       HW st = pair_field(*p, "stride", "stride_h", "stride_w", 1);
       HW pad = pair_field(*p, "pad", "pad_h", "pad_w", 0);
       if (p->boolean("global_pooling", false)) { k.h = in[2]; k.w = in[3]; }
-      if (k.h <= 0 || k.w <= 0) { *err = "layer '" + name + "': bad pooling_param"; return false; }
+      if (k.h <= 0 || k.w <= 0 || st.h <= 0 || st.w <= 0 || pad.h < 0 || pad.w < 0) {
+        *err = "layer '" + name + "': bad pooling_param";
+        return false;
+      }
       // pooling_layer.cpp: ceil((H + 2p - k) / s) + 1, clipped so the last window starts inside
       long oh = static_cast<long>(ceil(static_cast<float>(in[2] + 2 * pad.h - k.h) / st.h)) + 1;
       long ow = static_cast<long>(ceil(static_cast<float>(in[3] + 2 * pad.w - k.w) / st.w)) + 1;

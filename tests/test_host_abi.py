@@ -173,3 +173,107 @@ def test_jni_shim_type_checks_and_covers_the_18_natives():
         java = open("/root/reference/caffe-distri/src/main/java/com/yahoo/ml/jcaffe/CaffeNet.java").read()
         declared = set(re.findall(r"native\s+[\w\[\]]+\s+(\w+)\s*\(", java))
         assert declared == set(natives), declared ^ set(natives)
+
+
+def test_every_entry_point_survives_null_and_invalid_arguments(cos):
+    """Error behaviour at the boundary: a NULL handle / NULL pointers must come back as the failure value
+    (0 / -1 / NULL) with an error string -- never a crash (the JVM would die with the executor)."""
+    from caffeonspark_b200 import _lib
+    L = _lib.lib()
+    N = None
+    assert L.cos_net_local_addresses(N, None) == -1
+    assert L.cos_net_connect(N, None, 0) == 0
+    assert L.cos_net_sync(N) == 0
+    assert L.cos_net_init(N, 0, 1) == 0
+    assert L.cos_net_train(N, 0, None, 0) == 0
+    assert L.cos_net_predict(N, 0, None, 0, None, 0, None) == -1
+    assert L.cos_net_validation(N, None, 0) == 0
+    assert L.cos_net_aggregate_validation_outputs(N) == 0
+    for fn in (L.cos_net_device_id, L.cos_net_get_init_iter, L.cos_net_get_max_iter, L.cos_net_get_test_iter):
+        assert fn(N, 0) == -1 and fn(N, -1) == -1
+    assert L.cos_net_get_test_interval(N) == -1
+    assert L.cos_net_snapshot(N) == -1
+    assert L.cos_net_snapshot_filename(N, 0, 0, None, 0) == 0
+    assert L.cos_net_get_validation_output_blob_names(N, None) == -1
+    assert L.cos_net_get_validation_output_blobs(N, 1, None) == -1
+    assert L.cos_net_set_forward_backward(N, _lib.FORWARD_BACKWARD_FN(), None) == 0
+    assert L.cos_net_data(N, 0) is None and L.cos_net_diff(N, 0) is None and L.cos_net_history(N, 0) is None
+    assert L.cos_net_param_count(N) == -1
+    assert L.cos_net_shard(N, 0, None, None) == 0
+    assert L.cos_net_iter(N) == -1
+    assert L.cos_net_learning_rate(N) == 0.0 and L.cos_net_last_loss(N) == 0.0
+    assert L.cos_net_sync_step(N, 0, None) == 0
+    assert L.cos_net_all_gather_weights(N, 0, None) == 0
+    assert L.cos_net_synchronize(N) == 0
+    assert L.cos_net_set_option(N, b"grid", 1) == 0 and L.cos_net_get_option(N, b"grid") == -1
+    assert L.cos_net_last_kernel_ms(N) == -1.0 and L.cos_net_launch_count(N) == 0
+    L.cos_net_deallocate(N)
+    out = ctypes.c_void_p()
+    assert L.cos_net_allocate(None, None, None, 1, 1, 0, 1, 0, -1, 0, ctypes.byref(out)) == 0
+    assert b"solver_conf_file" in L.cos_last_error()
+    assert L.cos_net_allocate(b"/nonexistent.prototxt", b"", b"", 1, 1, 0, 1, 0, -1, 0, ctypes.byref(out)) == 0
+    assert L.cos_net_allocate_desc(None, 1, 1, 0, 1, 0, -1, ctypes.byref(out)) == 0
+    assert L.cos_net_allocate_desc(None, 1, 1, 0, 1, 0, -1, None) == 0
+    # adapter
+    assert L.cos_adapter_create(0, 0) is None and L.cos_adapter_create(2, 5) is None
+    assert L.cos_adapter_address(N) == b""
+    assert L.cos_adapter_connect(N, None, 0) == 0 and L.cos_adapter_barrier(N, 10) == 0
+    assert L.cos_adapter_offer_fd(N, b"k", -1, None, 0) == 0
+    assert L.cos_adapter_fetch_fd(N, 0, b"k", None, 0, 10) == -2
+    L.cos_adapter_destroy(N)
+    # pure helpers
+    assert L.cos_learning_rate(None, 0.1, 0.0, 0.0, 1, None, 0, 1, 0, None) == -1.0
+    assert L.cos_parse_solver(None, None, None, None, None, 0, None, None, 0, None, 0, None) == -1
+    assert L.cos_caffemodel_write(None, None, 0, None, None, None, None, None) == 0
+    assert L.cos_caffemodel_read(None, None, 0, None, 0) == -1
+    assert L.cos_solverstate_write(None, 0, 0, None, 0, None, None, None) == 0
+    assert L.cos_solverstate_read(None, None, None, None, 0, -1, None, 0) == -1
+
+
+def test_prototxt_parser_never_crashes_on_mutated_input(cos, tmp_path):
+    """Fuzz: truncations and byte flips of a valid net definition must parse or fail with an error, never crash."""
+    from caffeonspark_b200 import nets
+    rng = np.random.RandomState(3)
+    base = nets.net_prototxt("cifar10_quick")
+    solver = tmp_path / "s.prototxt"
+    netf = tmp_path / "n.prototxt"
+    solver.write_text('net: "n.prototxt"\nbase_lr: 0.01\nlr_policy: "fixed"\n')
+    ok = bad = 0
+    for trial in range(300):
+        b = bytearray(base.encode())
+        kind = trial % 3
+        if kind == 0:
+            b = b[:rng.randint(0, len(b))]
+        elif kind == 1:
+            for _ in range(rng.randint(1, 6)):
+                b[rng.randint(0, len(b))] = rng.randint(32, 127)
+        else:
+            i, j = sorted(rng.randint(0, len(b), 2))
+            del b[i:j]
+        netf.write_bytes(bytes(b))
+        try:
+            d = cos.parse_solver(str(solver))
+            assert all(c >= 0 for c in d.counts)
+            ok += 1
+        except cos.CosError:
+            bad += 1
+    assert ok + bad == 300 and bad > 0
+
+
+def test_parser_rejects_degenerate_geometry(cos, tmp_path):
+    head = ('layer { name: "d" type: "Input" top: "data" input_param { shape { dim: 2 dim: 4 dim: 8 dim: 8 } } }\n')
+    bad = ['layer { name: "c" type: "Convolution" bottom: "data" top: "c" convolution_param { num_output: 4 kernel_size: 3 stride: 0 } }',
+           'layer { name: "c" type: "Convolution" bottom: "data" top: "c" convolution_param { num_output: 4 kernel_size: 3 group: 3 } }',
+           'layer { name: "c" type: "Convolution" bottom: "data" top: "c" convolution_param { num_output: 4 kernel_size: 3 dilation: 0 } }',
+           'layer { name: "p" type: "Pooling" bottom: "data" top: "p" pooling_param { kernel_size: 2 stride: 0 } }',
+           'layer { name: "i" type: "InnerProduct" bottom: "data" top: "i" inner_product_param { num_output: 0 } }']
+    solver = tmp_path / "s.prototxt"
+    for layer in bad:
+        solver.write_text('base_lr: 0.1 lr_policy: "fixed" net_param { ' + head + layer + ' }')
+        with pytest.raises(cos.CosError, match="bad "):
+            cos.parse_solver(str(solver))
+    solver.write_text('base_lr: 0.1 lr_policy: "fixed" net_param { ' + head +
+                      'layer { name: "c" type: "Convolution" bottom: "data" top: "c" convolution_param '
+                      '{ num_output: 6 kernel_h: 3 kernel_w: 2 stride_h: 2 pad_w: 1 group: 2 bias_term: false } } }')
+    d = cos.parse_solver(str(solver))
+    assert d.counts == [6 * 2 * 3 * 2]
