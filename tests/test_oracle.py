@@ -178,3 +178,23 @@ def test_bf16_rounding_is_rne(oracle):
     import torch
     want = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
     assert np.array_equal(got, want)
+
+
+def test_baseline_config0_lenet_two_cpu_executors(oracle):
+    """BASELINE.json configs[0]: LeNet (lenet_memory_solver.prototxt hyper-parameters, P = 431,080), 2 CPU
+    executors, the reference's own socket sync -- run live (oracle/_ref) and matched bit for bit by the C
+    restatement.  This is the plumbing case that needs no GPU."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/ref_sync not built (no /root/reference on this box)")
+    counts = [500, 20, 25000, 50, 400000, 500, 5000, 10]
+    lm, dm = [1, 2] * 4, [1, 1] * 4
+    hp = dict(lr_policy="inv", base_lr=0.01, gamma=0.0001, power=0.75, momentum=0.9, weight_decay=0.0005)
+    ow, oh, fin = oracle.run_ref_dump(2, counts, lm, dm, iters=3, seed=1, **hp)
+    sim = oracle.Simulation(2, counts, lm, dm, seed=1, **hp)
+    for t in range(3):
+        sim.step()
+        for r in range(2):
+            w, h = sim.own(r)
+            assert np.array_equal(w, ow[t][r]) and np.array_equal(h, oh[t][r])
+    assert np.array_equal(fin[0], fin[1]) and np.array_equal(sim.consistent_weights(), fin[0])
+    assert sum(counts) == 431080 and oracle.chunk(431080, 2, 1) == (215540, 215540)
