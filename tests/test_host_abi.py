@@ -277,3 +277,23 @@ def test_parser_rejects_degenerate_geometry(cos, tmp_path):
                       '{ num_output: 6 kernel_h: 3 kernel_w: 2 stride_h: 2 pad_w: 1 group: 2 bias_term: false } } }')
     d = cos.parse_solver(str(solver))
     assert d.counts == [6 * 2 * 3 * 2]
+
+
+def test_gradient_producer_modules_match_the_flat_layout():
+    """The PyTorch stand-in for Net::ForwardBackward must expose its parameters in learnable_params() order with
+    exactly the blob sizes of the flat Params buffer, or aliasing data_/diff_ would be wrong."""
+    from caffeonspark_b200 import nets
+    for name, P in nets.EXPECTED_PARAM_COUNT.items():
+        counts, lm, dm, names = nets.layout(name)
+        mod = nets.torch_module(name)
+        sizes = [p.numel() for p in mod.parameters()]
+        assert sizes == counts and sum(sizes) == P, name
+        assert len(lm) == len(dm) == len(names) == len(counts)
+        # Caffe blob shapes == torch parameter shapes (conv: [out, in/g, kh, kw]; ip: [out, in]; bias: [out])
+        import torch
+        c, h, w = nets.NETS[name]["input"]
+        if name != "caffenet":  # a CPU forward/backward of the two small nets proves the module is well-formed
+            x = torch.rand(2, c, h, w)
+            loss = torch.nn.CrossEntropyLoss()(mod(x), torch.tensor([1, 3]))
+            loss.backward()
+            assert all(p.grad is not None and p.grad.shape == p.shape for p in mod.parameters())
