@@ -139,6 +139,7 @@ class CaffeNet {
   int opt_kernel_ = -1;  // -1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline
   int opt_timing_ = 1;
   int opt_nvls_ = 0;
+  int opt_small_grid_ = 0;      // experimental: size the grid by the reduce phase (see CaffeNet::launch)
   int opt_trace_ = 0;           // record %globaltimer at the phase boundaries of CTA 0 (diagnostics)
   int opt_initial_gather_ = 1;  // connect() runs the first on_start() (all-gather of weight shards)
   int64_t opt_timeout_ms_ = 20000;
