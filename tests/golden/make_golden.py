@@ -30,6 +30,14 @@ CASES = [
      dict(lr_policy="fixed", base_lr=0.001, momentum=0.9, weight_decay=0.004)),
     ("n4_lenet_head", 4, [500, 20, 2500, 50], [1, 2, 1, 2], [1, 1, 1, 1], 3, 16, False,
      dict(lr_policy="inv", base_lr=0.01, gamma=0.0001, power=0.75, momentum=0.9, weight_decay=0.0005)),
+    ("n5_multistep", 5, [333, 7, 64], [1, 2, 1], [1, 0, 1], 5, 17, False,
+     dict(lr_policy="multistep", base_lr=0.02, gamma=0.5, stepvalues=(2, 4), momentum=0.9, weight_decay=0.001)),
+    ("n6_poly", 6, [100, 1, 1, 1, 250], [1, 2, 1, 2, 1], [1, 1, 0, 0, 1], 3, 18, False,
+     dict(lr_policy="poly", base_lr=0.01, power=2.0, max_iter=10, momentum=0.5, weight_decay=0.0005)),
+    ("n7_plain_sgd", 7, [97, 11], [1, 1], [0, 0], 3, 19, False,
+     dict(lr_policy="exp", base_lr=0.05, gamma=0.9, momentum=0.0, weight_decay=0.0)),
+    ("n3_bf16_sigmoid", 3, [64, 64, 3], [1, 2, 1], [1, 1, 1], 3, 20, True,
+     dict(lr_policy="sigmoid", base_lr=0.01, gamma=-0.5, stepsize=2, momentum=0.9, weight_decay=0.004)),
 ]
 
 
