@@ -212,7 +212,12 @@ COS_API int cos_net_synchronize(cos_net* net);
  * 0 = LDG/STG vector kernel, 1 = TMA bulk-copy pipeline), "barrier_timeout_ms",
  * "one_shot_max_bytes", "timing" (CUDA events around each launch),
  * "initial_gather" (0 = connect() skips the first on_start(); the caller then
- * runs cos_net_all_gather_weights itself).  1/0. */
+ * runs cos_net_all_gather_weights itself), "nvls" (1 = reduce / broadcast
+ * through NVSwitch multicast when every rank can join; fp32 two-shot only;
+ * matches the reference to 1e-5, not bitwise), "trace" (record %globaltimer at
+ * the kernel's phase boundaries), "small_grid" (experimental grid sizing).
+ * Read-only via get_option: "resolved_algo", "resolved_kernel", "nvls_active",
+ * "transport", "default_grid", "trace_0".."trace_4".  1/0. */
 COS_API int cos_net_set_option(cos_net* net, const char* name, int64_t value);
 COS_API int64_t cos_net_get_option(cos_net* net, const char* name);
 
