@@ -297,3 +297,48 @@ def test_gradient_producer_modules_match_the_flat_layout():
             loss = torch.nn.CrossEntropyLoss()(mod(x), torch.tensor([1, 3]))
             loss.backward()
             assert all(p.grad is not None and p.grad.shape == p.shape for p in mod.parameters())
+
+
+def test_adapter_barrier_times_out_when_a_peer_never_arrives(cos):
+    """Failure detection on the control plane: the reference blocks forever in BlockingQueue::pop when a peer
+    dies; here the barrier returns false after its time-out and fetches fail cleanly when
+    the peer has gone away."""
+    import time
+    a, b = cos.PeerAdapter(2, 0), cos.PeerAdapter(2, 1)
+    addrs = [a.address(), b.address()]
+    import threading
+    oks = [None, None]
+    th = [threading.Thread(target=lambda r=r, ad=ad: oks.__setitem__(r, ad.connect(addrs))) for r, ad in enumerate((a, b))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert oks == [True, True]
+    t0 = time.time()
+    assert a.barrier(300) is False            # rank 1 never calls barrier()
+    assert 0.25 < time.time() - t0 < 5.0
+    assert "timed out" in cos.caffenet._err()
+    assert b.barrier(2000) is True            # ... the token rank 0 sent is still counted: b completes
+    b.close()                                 # peer goes away
+    with pytest.raises(cos.CosError):
+        a.fetch_fd(1, "anything", timeout_ms=300)
+    a.close()
+
+
+def test_bench_algorithmic_byte_model_matches_design():
+    """bench.py's roofline numerators are the formulas of DESIGN.md section 4."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    # importing bench.py redirects fd 1; only load the function's source instead
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    start = src.index("def algorithmic_bytes")
+    end = src.index("\ndef ", start + 10)
+    ns = {}
+    exec(src[start:end], ns)
+    f = ns["algorithmic_bytes"]
+    P = 60965224
+    assert f(P, 1, 0, 1, False) == (24 * P, 0)
+    assert f(P, 1, 0, 0, False) == (20 * P, 0)
+    hbm, nvl = f(P, 8, 1, 1, False)
+    assert nvl == pytest.approx(8 * P * 7 / 8)                   # (b_g + 4) * P * (N-1)/N, b_g = 4
+    assert f(P, 8, 1, 1, True)[1] == pytest.approx(6 * P * 7 / 8)  # bf16 wire
+    assert f(P, 4, 2, 1, False)[1] == 4 * P * 3                   # one-shot pulls (N-1) full gradients
+    assert spec is not None
