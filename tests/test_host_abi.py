@@ -89,6 +89,13 @@ def test_layout_parser_on_reference_config_files(cos):
             assert d.lr_policy == pol and d.batch_size == batch
     d = cos.parse_solver("/root/reference/data/bvlc_reference_solver.prototxt")
     assert d.decay_mult[1::2] == [0.0] * 8 and d.lr_mult[1::2] == [2.0] * 8  # biases: lr 2, decay 0
+    # every other CaffeOnSpark configuration on the path: DataFrame-fed LeNet and the JNI test's CaffeNet
+    # (fc8 with 2 outputs: 60,965,224 - (4,096,000 + 1000) + (4096 * 2 + 2))
+    assert cos.parse_solver("/root/reference/data/lenet_dataframe_solver.prototxt").param_count == 431080
+    t = cos.parse_solver("/root/reference/caffe-distri/src/test/resources/caffenet_solver.prototxt")
+    assert t.param_count == 60965224 - 4097000 + 8194 == 56876418 and t.batch_size == 4
+    with pytest.raises(cos.CosError, match="clip_gradients"):  # LRCN: clipping + LSTM are off the accelerated path
+        cos.parse_solver("/root/reference/data/lrcn_solver.prototxt")
 
 
 def test_parser_rejects_what_is_off_the_path(cos, tmp_path):
