@@ -198,3 +198,30 @@ def test_baseline_config0_lenet_two_cpu_executors(oracle):
             assert np.array_equal(w, ow[t][r]) and np.array_equal(h, oh[t][r])
     assert np.array_equal(fin[0], fin[1]) and np.array_equal(sim.consistent_weights(), fin[0])
     assert sum(counts) == 431080 and oracle.chunk(431080, 2, 1) == (215540, 215540)
+
+
+def test_c_oracle_agrees_with_independent_numpy_restatement(oracle):
+    """Two restatements written separately (C scalar loops vs vectorised numpy) must agree bit for bit on
+    random layouts, world sizes and hyper-parameters."""
+    from oracle import numpy_oracle as NO
+    rng = np.random.RandomState(2024)
+    for trial in range(40):
+        N = int(rng.randint(1, 9))
+        nb = int(rng.randint(1, 6))
+        counts = [int(c) for c in rng.randint(1, 200, nb)]
+        lm = [float(x) for x in rng.choice([1.0, 2.0, 0.5], nb)]
+        dm = [float(x) for x in rng.choice([1.0, 0.0, 0.25], nb)]
+        P = sum(counts)
+        rate, mom, wd = np.float32(rng.uniform(1e-4, 0.1)), np.float32(rng.choice([0.0, 0.5, 0.9])), \
+            np.float32(rng.choice([0.0, 5e-4, 4e-3]))
+        data = [(rng.randn(P) * 0.05).astype(np.float32) for _ in range(N)]
+        hist = [(rng.randn(P) * 0.01).astype(np.float32) for _ in range(N)]
+        grads = [(rng.randn(P) * 10 ** rng.uniform(-4, 0)).astype(np.float32) for _ in range(N)]
+        want_d, want_h = NO.step(data, grads, hist, counts, lm, dm, rate, mom, wd)
+        d2 = [x.copy() for x in data]
+        h2 = [x.copy() for x in hist]
+        g2 = [x.copy() for x in grads]
+        oracle.step(d2, g2, h2, counts, lm, dm, rate, mom, wd)
+        for r in range(N):
+            assert np.array_equal(d2[r].view(np.uint32), want_d[r].view(np.uint32)), (trial, N, r)
+            assert np.array_equal(h2[r].view(np.uint32), want_h[r].view(np.uint32)), (trial, N, r)
