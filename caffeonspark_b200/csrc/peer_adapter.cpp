@@ -9,6 +9,7 @@
 #include <sys/socket.h>
 #include <sys/time.h>
 #include <sys/un.h>
+#include <stdlib.h>
 #include <unistd.h>
 
 #include <chrono>
@@ -120,10 +121,18 @@ void set_timeouts(int fd, int ms) {
   setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
 }
 
-socklen_t abstract_addr(const std::string& name, struct sockaddr_un* sa) {
+// Endpoint names: "cosb200-..." lives in the abstract namespace (no file, vanishes with the process; needs a
+// shared NETWORK namespace); a name starting with '/' is a pathname socket (COS_SOCKET_DIR, for executors in
+// separate containers that share a directory).
+socklen_t endpoint_addr(const std::string& name, struct sockaddr_un* sa) {
   memset(sa, 0, sizeof(*sa));
   sa->sun_family = AF_UNIX;
   size_t n = name.size();
+  if (!name.empty() && name[0] == '/') {
+    if (n > sizeof(sa->sun_path) - 1) n = sizeof(sa->sun_path) - 1;
+    memcpy(sa->sun_path, name.data(), n);
+    return static_cast<socklen_t>(offsetof(struct sockaddr_un, sun_path) + n + 1);
+  }
   if (n > sizeof(sa->sun_path) - 2) n = sizeof(sa->sun_path) - 2;
   memcpy(sa->sun_path + 1, name.data(), n);  // sun_path[0] == 0 -> abstract namespace
   return static_cast<socklen_t>(offsetof(struct sockaddr_un, sun_path) + 1 + n);
@@ -145,19 +154,31 @@ PeerAdapter::PeerAdapter(int cluster_size, int rank)
     return;
   }
   std::random_device rd;
-  char name[96];
-  snprintf(name, sizeof(name), "cosb200-%ld-r%d-%08x%08x", static_cast<long>(getpid()), rank_, rd(), rd());
+  char leaf[96];
+  snprintf(leaf, sizeof(leaf), "cosb200-%ld-r%d-%08x%08x", static_cast<long>(getpid()), rank_, rd(), rd());
+  std::string name = leaf;
+  if (const char* dir = getenv("COS_SOCKET_DIR")) {
+    if (dir[0] == '/') {
+      name = std::string(dir) + "/" + leaf + ".sock";
+      path_ = name;
+      unlink(path_.c_str());
+    }
+  }
   struct sockaddr_un sa;
-  socklen_t slen = abstract_addr(name, &sa);
+  if (name.size() > sizeof(sa.sun_path) - 2) {
+    init_error_ = "socket path too long: " + name;
+    close(listen_fd_);
+    listen_fd_ = -1;
+    return;
+  }
+  socklen_t slen = endpoint_addr(name, &sa);
   if (bind(listen_fd_, reinterpret_cast<struct sockaddr*>(&sa), slen) < 0 || listen(listen_fd_, 64) < 0) {
     init_error_ = std::string("bind/listen: ") + strerror(errno);
     close(listen_fd_);
     listen_fd_ = -1;
     return;
   }
-  char addr[160];
-  snprintf(addr, sizeof(addr), "cosb200://%ld/%s", static_cast<long>(getpid()), name);
-  address_ = addr;
+  address_ = "cosb200://" + std::to_string(static_cast<long>(getpid())) + "/" + name;
   listener_ = std::thread(&PeerAdapter::listen_loop, this);
 }
 
@@ -174,6 +195,7 @@ PeerAdapter::~PeerAdapter() {
   for (auto& kv : offers_)
     if (kv.second.fd >= 0) close(kv.second.fd);
   for (auto* m : out_mu_) delete m;
+  if (!path_.empty()) unlink(path_.c_str());
 }
 
 void PeerAdapter::close_all() {
@@ -201,6 +223,10 @@ bool PeerAdapter::parse_address(const std::string& addr, long* pid, std::string*
   if (pid_s.empty() || pid_s.find_first_not_of("0123456789") != std::string::npos) return false;
   *pid = atol(pid_s.c_str());
   *name = addr.substr(slash + 1);
+  if (!name->empty() && (*name)[0] == '/') {  // pathname socket: .../cosb200-<pid>-r<rank>-<nonce>.sock
+    size_t leaf = name->find_last_of('/');
+    return name->compare(leaf + 1, 8, "cosb200-") == 0;
+  }
   return name->compare(0, 8, "cosb200-") == 0;
 }
 
@@ -295,7 +321,7 @@ bool PeerAdapter::connect(const std::vector<std::string>& addrs, std::string* er
       int s = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
       if (s < 0) break;
       struct sockaddr_un sa;
-      socklen_t slen = abstract_addr(name, &sa);
+      socklen_t slen = endpoint_addr(name, &sa);
       if (::connect(s, reinterpret_cast<struct sockaddr*>(&sa), slen) == 0) {
         fd = s;
       } else {

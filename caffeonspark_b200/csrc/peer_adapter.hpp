@@ -36,8 +36,8 @@ class PeerAdapter {
   int cluster_size() const { return cluster_size_; }
   int rank() const { return rank_; }
 
-  // "cosb200://<pid>/<abstract-socket-name>" (reference: "host:port",
-  // socket.hpp:28-37).
+  // "cosb200://<pid>/<endpoint>" (reference: "host:port", socket.hpp:28-37).  <endpoint> is an abstract
+  // unix-socket name, or an absolute socket path when COS_SOCKET_DIR is set.
   const std::string& address() const { return address_; }
   static bool parse_address(const std::string& addr, long* pid, std::string* name);
 
@@ -70,6 +70,7 @@ class PeerAdapter {
   const int cluster_size_;
   const int rank_;
   std::string address_, init_error_;
+  std::string path_;  // pathname socket to unlink (COS_SOCKET_DIR), empty for the abstract namespace
   int listen_fd_ = -1;
   bool stop_ = false;
   bool connected_ = false;

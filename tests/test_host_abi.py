@@ -349,3 +349,35 @@ def test_bench_algorithmic_byte_model_matches_design():
     assert f(P, 8, 1, 1, True)[1] == pytest.approx(6 * P * 7 / 8)  # bf16 wire
     assert f(P, 4, 2, 1, False)[1] == 4 * P * 3                   # one-shot pulls (N-1) full gradients
     assert spec is not None
+
+
+def test_adapter_pathname_sockets_for_separate_containers(cos, tmp_path, monkeypatch):
+    """COS_SOCKET_DIR: endpoints become socket files in a shared directory (executors that do not share a network
+    namespace cannot see each other's abstract sockets); same protocol, files removed on close."""
+    import threading
+    monkeypatch.setenv("COS_SOCKET_DIR", str(tmp_path))
+    ads = [cos.PeerAdapter(2, r) for r in range(2)]
+    addrs = [a.address() for a in ads]
+    assert all(a.startswith("cosb200://") and str(tmp_path) in a and a.endswith(".sock") for a in addrs)
+    assert len(list(tmp_path.glob("*.sock"))) == 2
+    oks = [None, None]
+    th = [threading.Thread(target=lambda r=r: oks.__setitem__(r, ads[r].connect(addrs) and ads[r].barrier(5000)))
+          for r in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert oks == [True, True]
+    fd = os.memfd_create("x")
+    os.write(fd, b"payload")
+    ads[1].offer_fd("k", fd, b"m")
+    got, meta = ads[0].fetch_fd(1, "k")
+    os.lseek(got, 0, os.SEEK_SET)
+    assert os.read(got, 16) == b"payload" and meta.startswith(b"m")
+    os.close(got)
+    os.close(fd)
+    [a.close() for a in ads]
+    assert list(tmp_path.glob("*.sock")) == []
+    monkeypatch.delenv("COS_SOCKET_DIR")
+    a = cos.PeerAdapter(2, 0)
+    assert not a.connect(["", "cosb200://1/" + str(tmp_path) + "/cosb200-1-r1-00.sock"])  # nobody there
+    assert not a.connect(["", "cosb200://1//etc/passwd"])                                   # not one of ours
+    a.close()
