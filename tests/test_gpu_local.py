@@ -132,7 +132,7 @@ def test_full_size_caffenet_properties(cos, oracle, kernel):
         assert_bits_equal(R.weights(0), sim.data[0], "caffenet weights")
         assert_bits_equal(R.history(0), sim.hist[0], "caffenet history")
         ms = R.nets[0].last_kernel_ms()
-        assert 0 < ms < 50
+        assert 0 < ms < 1.0, ms  # 24P = 1.46 GB in ~0.23 ms on a B200 (0.95+ of the HBM copy peak); loose 4x guard
     finally:
         R.close()
     desc0 = cos.SolverDesc([60965224], [1.0], [0.0], lr_policy="fixed", base_lr=0.1, momentum=0.9, weight_decay=0.5)
