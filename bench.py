@@ -163,6 +163,7 @@ def run_ours(args):
         net.set_option("algo", args.algo)
     net.set_option("kernel", args.kernel)
     net.set_option("nvls", int(args.nvls))
+    net.set_option("timing", 1)
     net.set_option("barrier_timeout_ms", 60000)
     prod = harness.make_producer(name, net)
     cl.start()
@@ -317,7 +318,7 @@ def run_ours(args):
                                f"PyTorch forward/backward + fused sync kernel",
                    "global_batch": world * batch, "parallelism": f"dp{world}",
                    "algo": {0: "local", 1: "two_shot", 2: "one_shot"}[mode], "grad_dtype": args.grad_dtype,
-                   "kernel": {0: "ldg_stg_vector", 1: "tma_bulk_pipeline"}[int(net.get_option("resolved_kernel"))],
+                   "kernel": KERNEL_NAMES[int(net.get_option("resolved_kernel"))],
                    "nvls": bool(net.get_option("nvls_active")),
                    "producer": "cuda_graph" if graph is not None else "eager",
                    "l2": "flushed between steps (256 MiB write outside the timed events)" if need_flush
@@ -329,8 +330,9 @@ def run_ours(args):
                 "last_loss": last_loss},
         "gpu_launches": int(launches), "e2e_gpu_launches": int(e2e_launches),
         "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fused_sync_sgd_tma_kernel" if
-                     int(net.get_option("resolved_kernel")) else "fused_sync_sgd_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": {0: "fused_sync_sgd_kernel", 1: "fused_sync_sgd_tma_kernel",
+                                2: "fused_sync_sgd_push_kernel", 3: "fused_sync_sgd_nvls_kernel"}[
+                         int(net.get_option("resolved_kernel"))], "kernel_ms": k_ms,
                      "algorithmic_bytes": alg, "peak_source": (peak_kind + " MEASURED_PEAKS.json hbm_gbs") if
                      world == 1 else "B200_PROFILING.md measured peer copy per direction"},
         "split_ms": {"forward_backward": fb_ms, "fused_sync_kernel": k_ms},
@@ -377,6 +379,7 @@ def kernel_rooflines(C, nets, peaks, world, kernel=-1):
         net = C.CaffeNet(desc, "", "", 1, 1, 0, True, 0, torch.cuda.current_device() - 1, 0)
         net.connect([])
         net.set_option("kernel", kernel)
+        net.set_option("timing", 1)
         P = net.param_count()
         net.diff().normal_(0, 0.01)
         ms = []
@@ -494,8 +497,32 @@ def run_reference(args):
     emit(out)
 
 
+SWEEP_VARIANTS = {
+    # name: (algo, options set BEFORE connect)
+    "ldg": (1, {"kernel": 0, "nvls": 0}),
+    "tma": (1, {"kernel": 1, "nvls": 0}),
+    "push": (1, {"kernel": 2, "nvls": 0}),
+    "push1": (1, {"kernel": 2, "nvls": 0, "push_vecs": 1}),
+    "push4": (1, {"kernel": 2, "nvls": 0, "push_vecs": 4}),
+    "push8": (1, {"kernel": 2, "nvls": 0, "push_vecs": 8}),
+    "ldg1s": (2, {"kernel": 0, "nvls": 0}),
+    "tma1s": (2, {"kernel": 1, "nvls": 0}),
+    "nvls1": (1, {"kernel": 3, "nvls": 1, "nvls_unroll": 1}),
+    "nvls2": (1, {"kernel": 3, "nvls": 1, "nvls_unroll": 2}),
+    "nvls4": (1, {"kernel": 3, "nvls": 1, "nvls_unroll": 4}),
+    "nvls8": (1, {"kernel": 3, "nvls": 1, "nvls_unroll": 8}),
+    "nvls1p": (1, {"kernel": 3, "nvls": 1, "nvls_unroll": 1, "nvls_p2p": 1}),
+    "nvls2p": (1, {"kernel": 3, "nvls": 1, "nvls_unroll": 2, "nvls_p2p": 1}),
+    "nvls3p": (1, {"kernel": 3, "nvls": 1, "nvls_unroll": 3, "nvls_p2p": 1}),
+    "nvls4p": (1, {"kernel": 3, "nvls": 1, "nvls_unroll": 4, "nvls_p2p": 1}),
+    "auto": (0, {}),
+}
+KERNEL_NAMES = {0: "ldg_stg_vector", 1: "tma_bulk_pipeline", 2: "push_store", 3: "nvls_multimem"}
+
+
 def run_sweep(args):
-    """Config 5: all-reduce message sweep 64 KiB - 512 MiB (single segment)."""
+    """Config 5: all-reduce message sweep 64 KiB - 512 MiB (single segment), every kernel variant asked for
+    with --variants, next to NCCL's all-reduce of the same message (which does not include the update)."""
     import torch
     import torch.distributed as dist
     import caffeonspark_b200 as C
@@ -505,27 +532,39 @@ def run_sweep(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     rows = []
-    sizes = [64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20, 512 << 20]
+    if args.sizes:
+        sizes = [int(float(x) * (1 << 20)) // 4 * 4 for x in args.sizes.split(",")]
+    else:
+        sizes = [64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20, 512 << 20]
     sizes = [b for b in sizes if args.sweep_min_bytes <= b <= args.sweep_max_bytes]
+    names = args.variants.split(",") if args.variants else (["ldg", "tma", "push", "auto"] if world > 1 else ["ldg", "tma"])
+    if args.nvls == 1 and "nvls4" not in names:
+        names.append("nvls4")
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for S in sizes:
         P = S // 4
-        variants = [(a, k) for a in ((1, 2) if (world > 1 and S <= (4 << 20)) else (1,)) for k in (0, 1)]
-        if world > 1 and args.nvls:
-            variants.append((1, 2))  # two-shot through NVLS (kernel id 2 = LDG kernel + multimem)
         nccl_ms = None
-        for algo, kern in variants:
-            desc = C.SolverDesc([P], lr_policy="fixed", base_lr=0.01, momentum=0.9, weight_decay=0.0005)
+        for vname in names:
+            algo, opts = SWEEP_VARIANTS[vname]
+            if world == 1 and (vname.startswith(("push", "nvls")) or algo == 2):
+                continue
+            desc = C.SolverDesc([P], lr_policy="fixed", base_lr=0.01, momentum=0.9, weight_decay=0.0005,
+                                grad_dtype=args.grad_dtype)
             cl = harness.Cluster(desc, rank=rank, world=world, device=local)
             net = cl.net
-            net.set_option("kernel", min(kern, 1) if kern != 2 else 0)
-            net.set_option("nvls", int(kern == 2))
-            if world > 1:
+            for k, v in opts.items():
+                net.set_option(k, v)
+            if world > 1 and algo:
                 net.set_option("algo", algo)
+            net.set_option("zero_diff", int(args.zero_diff))
+            net.set_option("timing", 1)
             net.set_option("barrier_timeout_ms", 60000)
             cl.start()
             net.diff().normal_(0, 0.01)
             ms = []
             for i in range(args.warmup + args.steps):
+                if S < (64 << 20):
+                    flush_buf.zero_()
                 torch.cuda.synchronize()
                 if world > 1:
                     dist.barrier()
@@ -546,6 +585,7 @@ def run_sweep(args):
                 dist.barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 20
+            net.set_option("timing", 0)
             st = torch.cuda.Stream()  # explicit stream: handle 0 would mean "the net's own stream"
             with torch.cuda.stream(st):
                 if not net.sync_step(0, st.cuda_stream):
@@ -563,14 +603,19 @@ def run_sweep(args):
                 t = torch.tensor([piped], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 piped = float(t.item())
-            row = {"bytes": S, "algo": {1: "two_shot", 2: "one_shot"}[algo] if world > 1 else "local",
-                   "kernel": {0: "ldg", 1: "tma", 2: "nvls" if net.get_option("nvls_active") else "nvls-unavailable"}[kern],
+            row = {"bytes": S, "variant": vname,
+                   "algo": {0: "local", 1: "two_shot", 2: "one_shot"}[int(net.get_option("resolved_algo"))],
+                   "kernel": KERNEL_NAMES[int(net.get_option("resolved_kernel"))],
+                   "nvls_active": bool(net.get_option("nvls_active")), "grad_dtype": args.grad_dtype,
+                   "zero_diff": bool(args.zero_diff),
                    "kernel_ms": k, "min_ms": min(ms), "pipelined_ms": piped}
-            if args.trace and kern == 0:
-                # where the time goes inside one launch (CTA 0, %globaltimer): launch->A, A->phase1 end, B, zero
+            if args.trace and int(net.get_option("resolved_kernel")) != 1:
+                # where the time goes inside one launch (CTA 0, %globaltimer); stamps per kernel:
+                #  ldg/nvls: start, after barrier A, after reduce+update+push, after barrier B, after zero
+                #  push    : start, after scatter-push, after barrier A, after reduce+update+push, after barrier B
                 net.set_option("trace", 1)
                 tr = []
-                for _ in range(5):
+                for _ in range(7):
                     torch.cuda.synchronize()
                     if world > 1:
                         dist.barrier()
@@ -579,7 +624,7 @@ def run_sweep(args):
                     t = [net.get_option(f"trace_{i}") for i in range(5)]
                     tr.append([(t[i + 1] - t[i]) / 1e3 for i in range(4)])
                 net.set_option("trace", 0)
-                row["trace_us_barrierA_phase1_barrierB_zero"] = [sorted(c)[len(c) // 2] for c in zip(*tr)]
+                row["trace_us"] = [sorted(c)[len(c) // 2] for c in zip(*tr)]
             if world > 1:
                 row["bus_gbs"] = S * 2 * (world - 1) / world / (k * 1e-3) / 1e9
             if world > 1 and nccl_ms is None:
@@ -597,12 +642,19 @@ def run_sweep(args):
                     if i >= args.warmup:
                         evs.append(a.elapsed_time(b))
                 nccl_ms = sorted(evs)[len(evs) // 2]
+                t = torch.tensor([nccl_ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                nccl_ms = float(t.item())
                 del buf
             if world > 1:
                 row["nccl_allreduce_ms"] = nccl_ms
             else:
-                row["hbm_gbs"] = 24 * P / (k * 1e-3) / 1e9
+                row["hbm_gbs"] = (24 if args.zero_diff else 20) * P / (k * 1e-3) / 1e9
             rows.append(row)
+            if rank == 0:
+                print("[sweep] %8d KiB %-7s %-18s nvls=%d  %.1f us (min %.1f, piped %.1f)  nccl %s  trace %s" % (
+                    S >> 10, vname, row["kernel"], row["nvls_active"], k * 1e3, min(ms) * 1e3, piped * 1e3,
+                    "%.1f us" % (nccl_ms * 1e3) if nccl_ms else "-", row.get("trace_us")), file=sys.stderr)
             net.deallocate()
             if world > 1:
                 dist.barrier()
@@ -622,13 +674,16 @@ def main():
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 two-shot, 2 one-shot")
     ap.add_argument("--kernel", type=int, default=-1, help="-1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline")
-    ap.add_argument("--nvls", action="store_true", help="reduce/broadcast through NVSwitch multicast (fp32 two-shot)")
+    ap.add_argument("--nvls", type=int, default=-1, help="NVSwitch multicast reduce/broadcast: -1 auto, 0 off, 1 on")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", action="store_true", default=True)
     ap.add_argument("--no-kernels", dest="kernels", action="store_false")
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--trace", action="store_true", help="sweep: per-phase timestamps of the LDG kernel")
+    ap.add_argument("--variants", default="", help="sweep: comma list of " + ",".join(SWEEP_VARIANTS))
+    ap.add_argument("--sizes", default="", help="sweep: comma list of message sizes in MiB (fractions allowed)")
+    ap.add_argument("--zero-diff", type=int, default=1, help="sweep: fold ClearParamDiffs into the kernel")
     ap.add_argument("--sweep-min-bytes", type=int, default=0)
     ap.add_argument("--sweep-max-bytes", type=int, default=1 << 40)
     args = ap.parse_args()

@@ -155,6 +155,11 @@ bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::str
   off = align_up(off + fbytes, 4096);
   off_wire_ = off;
   if (spec_.grad_dtype == COS_GRAD_BF16) off = align_up(off + static_cast<size_t>(count_) * 2, 4096);
+  off_recv_ = off;
+  if (world_ > 1) {  // receive slots of the push kernel: one per source rank, ~P/N elements each (<= 4P bytes in all)
+    recv_stride_ = push_recv_stride(count_, world_);
+    off = align_up(off + static_cast<size_t>(world_) * recv_stride_ * (spec_.grad_dtype == COS_GRAD_BF16 ? 2 : 4), 4096);
+  }
   const char* tr = getenv("COS_PEER_TRANSPORT");
   const bool prefer_vmm = peer_mappable && !(tr && strcmp(tr, "ipc") == 0);
   if (!arena_.create(dev, off, prefer_vmm, err)) return false;
@@ -168,6 +173,8 @@ bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::str
   peer_wire_[rank_] = wire_;
   peer_hist_[rank_] = hist_;
   peer_flags_[rank_] = reinterpret_cast<uint32_t*>(base);
+  recv_ = recv_stride_ ? static_cast<void*>(base + off_recv_) : nullptr;
+  peer_recv_[rank_] = recv_;
 
   // blob (segment) table: cumulative ends + multipliers
   std::vector<uint64_t> ends;
@@ -230,14 +237,28 @@ int CaffeNet::resolved_algo() const {
   return static_cast<int64_t>(count_ * sizeof(float)) <= opt_one_shot_max_bytes_ ? kModeOneShot : kModeTwoShot;
 }
 
-// Kernel variant: measured on B200 (profiles/r01_sweep_*.json) the TMA bulk-copy pipeline wins once the
-// message is large enough to be NVLink-bandwidth bound; the LDG/STG kernel has the lower fixed cost.
-// Depends only on (world, P), so every rank resolves the same variant.
+// Kernel variant (0 LDG/STG pull, 1 TMA bulk-copy pull, 2 push, 3 NVLS).  Depends only on (world, P, wire
+// dtype, options, NVLS team) -- all identical on every rank -- so every rank resolves the same variant, which
+// the per-CTA barriers require.  AUTO, from the B200 measurements under profiles/:
+//   * N >= 4, fp32 wire, multicast team up, 4P >= nvls_min_bytes: NVLS (half the NVLink bytes of P2P);
+//   * bf16 wire: push (the only variant whose cast costs no extra pass);
+//   * 4P < push_max_bytes: push (stores only, two store round trips on the critical path);
+//   * otherwise the TMA pull pipeline.
+// A forced variant that cannot run the current mode falls back to AUTO's choice.
 int CaffeNet::resolved_kernel() const {
-  if (nvls_active_ && spec_.grad_dtype == COS_GRAD_FP32 && resolved_algo() == kModeTwoShot) return 0;  // NVLS lives there
-  if (opt_kernel_ >= 0) return opt_kernel_;
+  const int algo = resolved_algo();
+  const bool fp32 = spec_.grad_dtype == COS_GRAD_FP32;
+  const int64_t bytes = static_cast<int64_t>(count_ * sizeof(float));
+  const bool nvls_ok = nvls_active_ && fp32 && algo == kModeTwoShot;
+  const bool push_ok = world_ > 1 && algo == kModeTwoShot && recv_stride_ > 0;
+  if (opt_kernel_ == 0 || opt_kernel_ == 1) return opt_kernel_;
+  if (opt_kernel_ == 2 && push_ok) return 2;
+  if (opt_kernel_ == 3 && nvls_ok) return 3;
   if (world_ == 1) return 0;
-  return count_ * sizeof(float) >= (2u << 20) ? 1 : 0;
+  if (algo != kModeTwoShot) return bytes >= (2 << 20) ? 1 : 0;
+  if (nvls_ok && (opt_nvls_ == 1 || (world_ >= 4 && bytes >= opt_nvls_min_bytes_))) return 3;
+  if (push_ok && (!fp32 || bytes < opt_push_max_bytes_)) return 2;
+  return bytes >= (2 << 20) ? 1 : 0;
 }
 
 float CaffeNet::current_rate() {
@@ -264,7 +285,11 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
     p.diff[r] = peer_diff_[r];
     p.wire[r] = peer_wire_[r];
     p.flags[r] = peer_flags_[r];
+    p.recv[r] = peer_recv_[r];
   }
+  p.recv_stride = recv_stride_;
+  p.nvls_unroll = opt_nvls_unroll_;
+  p.nvls_p2p = opt_nvls_p2p_;
   p.use_nvls = nvls_active_ ? 1 : 0;
   p.mc_data = nvls_active_ ? reinterpret_cast<float*>(mc_base_ + off_data_) : nullptr;
   p.mc_diff = nvls_active_ ? reinterpret_cast<const float*>(mc_base_ + off_diff_) : nullptr;
@@ -302,9 +327,14 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
     const uint64_t cap = static_cast<uint64_t>(default_sync_grid(device_));
     grid = static_cast<int>(need < 1 ? 1 : (need > cap ? cap : need));
   }
-  cudaError_t e = (resolved_kernel() == 1 && mode != kModeAllGather)
-                      ? launch_fused_sync_sgd_tma(p, grid, stream)
-                      : launch_fused_sync_sgd(p, grid, opt_block_, stream);
+  const int kern = (mode == kModeAllGather) ? 0 : resolved_kernel();
+  cudaError_t e;
+  switch (kern) {
+    case 1: e = launch_fused_sync_sgd_tma(p, grid, stream); break;
+    case 2: e = launch_fused_sync_sgd_push(p, grid, opt_block_, opt_push_vecs_, stream); break;
+    case 3: e = launch_fused_sync_sgd_nvls(p, grid, stream); break;
+    default: e = launch_fused_sync_sgd(p, grid, opt_block_, stream); break;
+  }
   if (e != cudaSuccess) {
     *err = rt_err("fused_sync_sgd launch", e);
     return false;
@@ -351,6 +381,12 @@ bool CaffeNet::check_status(std::string* err) {
   if (s == 0) return true;
   *reinterpret_cast<volatile int*>(status_) = 0;
   std::ostringstream os;
+  if (s == 300) {  // fused_sync_sgd_tma.cu: an mbarrier never completed (a bulk copy was lost or a peer died mid-tile)
+    os << "device-side TMA pipeline timed out after " << opt_timeout_ms_
+       << " ms waiting for a bulk copy to complete (status 300)";
+    *err = os.str();
+    return false;
+  }
   int which = (s - 100) / 32, peer = (s - 100) % 32;
   os << "device-side barrier " << (which == 0 ? "A (gradients ready)" : "B (weights landed)") << " timed out after "
      << opt_timeout_ms_ << " ms waiting for rank " << peer << " (status " << s << ")";
@@ -443,7 +479,12 @@ bool CaffeNet::set_option(const std::string& name, int64_t v, std::string* err) 
   else if (name == "block") opt_block_ = static_cast<int>(v);
   else if (name == "kernel") opt_kernel_ = static_cast<int>(v);
   else if (name == "timing") opt_timing_ = v != 0;
-  else if (name == "nvls") opt_nvls_ = v != 0;
+  else if (name == "nvls") opt_nvls_ = v < 0 ? -1 : (v != 0);
+  else if (name == "nvls_unroll") opt_nvls_unroll_ = static_cast<int>(v);
+  else if (name == "nvls_p2p") opt_nvls_p2p_ = static_cast<int>(v);
+  else if (name == "push_vecs") opt_push_vecs_ = static_cast<int>(v);
+  else if (name == "push_max_bytes") opt_push_max_bytes_ = v;
+  else if (name == "nvls_min_bytes") opt_nvls_min_bytes_ = v;
   else if (name == "barrier_timeout_ms") opt_timeout_ms_ = v;
   else if (name == "one_shot_max_bytes") opt_one_shot_max_bytes_ = v;
   else if (name == "iter") { iter_ = static_cast<int>(v); }
@@ -468,6 +509,11 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "timing") return opt_timing_;
   if (name == "nvls") return opt_nvls_;
   if (name == "nvls_active") return nvls_active_ ? 1 : 0;
+  if (name == "nvls_unroll") return opt_nvls_unroll_;
+  if (name == "nvls_p2p") return opt_nvls_p2p_;
+  if (name == "push_vecs") return opt_push_vecs_;
+  if (name == "push_max_bytes") return opt_push_max_bytes_;
+  if (name == "nvls_min_bytes") return opt_nvls_min_bytes_;
   if (name == "barrier_timeout_ms") return opt_timeout_ms_;
   if (name == "one_shot_max_bytes") return opt_one_shot_max_bytes_;
   if (name == "initial_gather") return opt_initial_gather_;
@@ -743,9 +789,14 @@ bool NvlinkCaffeNet::connect(const std::vector<std::string>& addresses, std::str
     peer_diff_[peer] = reinterpret_cast<const float*>(base + off_diff_);
     peer_hist_[peer] = reinterpret_cast<const float*>(base + off_hist_);
     peer_wire_[peer] = wire_ ? reinterpret_cast<uint16_t*>(base + off_wire_) : nullptr;
+    peer_recv_[peer] = recv_stride_ ? static_cast<void*>(base + off_recv_) : nullptr;
   }
   connected_ = true;
-  if (opt_nvls_) setup_nvls(timeout);
+  // NVLS multicast team: on request, or by default where it pays (N >= 4, message >= nvls_min_bytes, fp32 wire).
+  // The decision uses only values that are identical on every rank.
+  const bool want_nvls = opt_nvls_ == 1 || (opt_nvls_ < 0 && world_ >= 4 && spec_.grad_dtype == COS_GRAD_FP32 &&
+                                            static_cast<int64_t>(count_ * sizeof(float)) >= opt_nvls_min_bytes_);
+  if (want_nvls) setup_nvls(timeout);
   // everyone has mapped everyone; then the first on_start(): all-gather of the
   // owners' weight shards (socket_sync_cpu.cpp:102-105), so that all ranks
   // start from the same weights even if they were initialised differently.

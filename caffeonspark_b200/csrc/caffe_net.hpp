@@ -99,7 +99,9 @@ class CaffeNet {
 
   // Params<Dtype> (parallel.hpp:22-45): flat buffers, inside the peer-mappable arena
   DeviceArena arena_;
-  size_t off_data_ = 0, off_diff_ = 0, off_hist_ = 0, off_wire_ = 0;
+  size_t off_data_ = 0, off_diff_ = 0, off_hist_ = 0, off_wire_ = 0, off_recv_ = 0;
+  uint64_t recv_stride_ = 0;       // elements per receive slot of the push kernel (0: no receive region)
+  void* recv_ = nullptr;           // [world][recv_stride_] fp32 or bf16: the reference's diff_recv_ scratch, on device
   float* data_ = nullptr;
   float* diff_ = nullptr;
   uint16_t* wire_ = nullptr;
@@ -119,6 +121,7 @@ class CaffeNet {
   uint16_t* peer_wire_[kMaxRanks] = {};
   const float* peer_hist_[kMaxRanks] = {};
   uint32_t* peer_flags_[kMaxRanks] = {};
+  void* peer_recv_[kMaxRanks] = {};
   bool connected_ = false;
   bool nvls_active_ = false;        // multicast object bound on every rank (NvlinkCaffeNet::setup_nvls)
   char* mc_base_ = nullptr;         // multicast VA of the arena
@@ -136,9 +139,14 @@ class CaffeNet {
   int opt_algo_ = COS_ALGO_AUTO;
   int opt_zero_diff_ = 1;
   int opt_grid_ = 0, opt_block_ = 0;
-  int opt_kernel_ = -1;  // -1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline
-  int opt_timing_ = 1;
-  int opt_nvls_ = 0;
+  int opt_kernel_ = -1;  // -1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline, 2 push, 3 NVLS (multimem)
+  int opt_timing_ = 0;   // CUDA events around every launch (cos_net_last_kernel_ms); benchmarks turn it on
+  int opt_nvls_ = -1;    // -1 auto (multicast team when world >= 4 and 4P >= nvls_min_bytes), 0 off, 1 on
+  int opt_nvls_unroll_ = 4;     // switch loads in flight per thread
+  int opt_nvls_p2p_ = 0;        // 1: one plain-P2P vector per nvls_unroll switch vectors (link + switch both busy)
+  int opt_push_vecs_ = 2;       // push kernel: float4 vectors per thread of the owner phase (sizes the grid)
+  int64_t opt_push_max_bytes_ = 8 << 20;   // AUTO: push kernel below this message size (4P bytes), fp32 wire
+  int64_t opt_nvls_min_bytes_ = 2 << 20;   // AUTO: NVLS kernel at or above this message size when world >= 4
   int opt_small_grid_ = 0;      // experimental: size the grid by the reduce phase (see CaffeNet::launch)
   int opt_trace_ = 0;           // record %globaltimer at the phase boundaries of CTA 0 (diagnostics)
   int opt_initial_gather_ = 1;  // connect() runs the first on_start() (all-gather of weight shards)

@@ -96,10 +96,8 @@ __device__ __forceinline__ float4 reduce_vec_any(const SyncParams& p, int s, uin
 // ------------------------------------------------------------- the kernel
 
 // N = compile-time world size (0 = runtime world, any size up to kMaxRanks).
-// NVLS = reduce through the switch (multimem.ld_reduce) and broadcast the new
-// weights with one multicast store; the sum order is then the switch's, so the
-// result matches the reference to rounding (<= 1e-5 relative), not bit for bit.
-template <int N, bool BF16, bool NVLS = false>
+// (The in-switch NVLS variant lives in fused_sync_sgd_nvls.cu.)
+template <int N, bool BF16>
 __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(const SyncParams p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_abort;
@@ -205,34 +203,7 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
         r = shard_range(p.count, world, s);
       }
       if (tid < r.nvec) cur.seek((r.vec_lo + tid) << 2);
-      if (NVLS) {
-        // switch loads have the longest latency on the path: keep kNvlsUnroll of them (plus the local w/h
-        // loads) in flight per thread.  j and j + u*stride belong to the same CTA, so the partition holds.
-        constexpr int kNvlsUnroll = 4;
-        for (uint64_t j0 = tid; j0 < r.nvec; j0 += stride * kNvlsUnroll) {
-          float4 sum[kNvlsUnroll];
-#pragma unroll
-          for (int u = 0; u < kNvlsUnroll; ++u) {
-            const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-            if (j < r.nvec) sum[u] = mc_ld_reduce(p.mc_diff + ((r.vec_lo + j) << 2));
-          }
-#pragma unroll
-          for (int u = 0; u < kNvlsUnroll; ++u) {
-            const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-            if (j < r.nvec) {
-              const uint64_t i = (r.vec_lo + j) << 2;
-              float4 w = *reinterpret_cast<const float4*>(wl + i);  // local: short latency, hidden by the other warps
-              float4 h = *reinterpret_cast<const float4*>(hl + i);
-              const float4 g = make_float4(__fmul_rn(p.inv_scale, sum[u].x), __fmul_rn(p.inv_scale, sum[u].y),
-                                           __fmul_rn(p.inv_scale, sum[u].z), __fmul_rn(p.inv_scale, sum[u].w));
-              sgd_vec(p, cur, i, g, w, h);
-              *reinterpret_cast<float4*>(hl + i) = h;
-              mc_st(p.mc_data + i, w);  // one store: own data_ and every peer's data_
-            }
-          }
-        }
-      }
-      for (uint64_t j = NVLS ? r.nvec : tid; j < r.nvec; j += stride) {
+      for (uint64_t j = tid; j < r.nvec; j += stride) {
         const uint64_t i = (r.vec_lo + j) << 2;
         float4 w = *reinterpret_cast<const float4*>(wl + i);
         float4 h = *reinterpret_cast<const float4*>(hl + i);
@@ -245,21 +216,13 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
             g.z = bf16_bits_to_float(float_to_bf16_bits(g.z));
             g.w = bf16_bits_to_float(float_to_bf16_bits(g.w));
           }
-        } else if (NVLS) {
-          const float4 sum = mc_ld_reduce(p.mc_diff + i);  // in-switch sum over all ranks, then the 1/N scale
-          g = make_float4(__fmul_rn(p.inv_scale, sum.x), __fmul_rn(p.inv_scale, sum.y),
-                          __fmul_rn(p.inv_scale, sum.z), __fmul_rn(p.inv_scale, sum.w));
         } else {
           g = reduce_vec_any<N, BF16>(p, s, i);
         }
         sgd_vec(p, cur, i, g, w, h);
         *reinterpret_cast<float4*>(hl + i) = h;
-        if (NVLS) {
-          mc_st(p.mc_data + i, w);  // one store: own data_ and every peer's data_
-        } else {
-          *reinterpret_cast<float4*>(wl + i) = w;
-        }
-        if (push && !NVLS) {
+        *reinterpret_cast<float4*>(wl + i) = w;
+        if (push) {
 #pragma unroll
           for (int q = 1; q < (N > 0 ? N : 1); ++q) {
             int dst = rank + q;
@@ -355,9 +318,7 @@ uint64_t host_mix64(uint64_t z) {
 
 template <int N>
 cudaError_t launch_n(const SyncParams& p, int grid, int block, size_t smem, cudaStream_t stream) {
-  if (N == 0 && p.use_nvls && p.mode == kModeTwoShot && !p.grad_bf16)
-    fused_sync_sgd_kernel<0, false, true><<<grid, block, smem, stream>>>(p);
-  else if (p.grad_bf16) fused_sync_sgd_kernel<N, true><<<grid, block, smem, stream>>>(p);
+  if (p.grad_bf16) fused_sync_sgd_kernel<N, true><<<grid, block, smem, stream>>>(p);
   else fused_sync_sgd_kernel<N, false><<<grid, block, smem, stream>>>(p);
   return cudaGetLastError();
 }
@@ -391,8 +352,7 @@ cudaError_t launch_fused_sync_sgd(const SyncParams& p, int grid, int block, cuda
   if (need < 1) need = 1;
   if (static_cast<uint64_t>(grid) > need) grid = static_cast<int>(need);
   size_t smem = p.nseg <= kMaxSegSmem ? static_cast<size_t>(p.nseg) * (sizeof(uint64_t) + 2 * sizeof(float)) : 0;
-  const bool nvls = p.use_nvls && p.mode == kModeTwoShot && !p.grad_bf16 && p.mc_data && p.mc_diff;
-  const int n = (p.mode == kModeLocal || p.mode == kModeAllGather || nvls) ? 0 : p.world;
+  const int n = (p.mode == kModeLocal || p.mode == kModeAllGather) ? 0 : p.world;
   switch (n) {
     case 2: return launch_n<2>(p, grid, block, smem, stream);
     case 3: return launch_n<3>(p, grid, block, smem, stream);

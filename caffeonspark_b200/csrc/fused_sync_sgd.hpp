@@ -37,9 +37,13 @@ struct SyncParams {
   const float* diff[kMaxRanks];     // diff_ of every rank (fp32)
   uint16_t* wire[kMaxRanks];        // bf16 gradient wire buffer of every rank
   uint32_t* flags[kMaxRanks];       // flag region of every rank
+  void* recv[kMaxRanks];            // push kernel: receive slots of every rank ([src][recv_stride] fp32 or bf16)
+  uint64_t recv_stride;             // elements per receive slot
   float* mc_data;                   // NVLS: multicast address of data_ (a store lands on every rank)
   const float* mc_diff;             // NVLS: multicast address of diff_ (a load returns the in-switch sum)
-  int use_nvls;                     // two-shot fp32 only: multimem.ld_reduce / multimem.st instead of P2P
+  int use_nvls;                     // two-shot only: multimem.ld_reduce / multimem.st instead of P2P
+  int nvls_unroll;                  // NVLS kernel: switch loads in flight per thread (1, 2, 4, 8)
+  int nvls_p2p;                     // NVLS kernel: of every (nvls_unroll + nvls_p2p) vectors this many go over plain P2P
   float* hist;                      // local SGD history (momentum buffer)
   const uint64_t* seg_end;          // [nseg] cumulative blob ends (exclusive)
   const float* seg_lr_mult;         // [nseg]
@@ -58,6 +62,15 @@ struct SyncParams {
 cudaError_t launch_fused_sync_sgd(const SyncParams& p, int grid, int block, cudaStream_t stream);
 // Launches the TMA (cp.async.bulk) pipelined variant of the same computation.
 cudaError_t launch_fused_sync_sgd_tma(const SyncParams& p, int grid, cudaStream_t stream);
+// Launches the push variant (two-shot only): gradient shards are STORED into the owners' receive slots
+// (fp32 -> bf16 cast in registers), reduced from local memory, weights pushed back.  vecs_per_thread sizes
+// the grid (0 = default).
+cudaError_t launch_fused_sync_sgd_push(const SyncParams& p, int grid, int block, int vecs_per_thread,
+                                       cudaStream_t stream);
+// Launches the NVLS (multimem) variant with optional P2P share (fused_sync_sgd_nvls.cu).
+cudaError_t launch_fused_sync_sgd_nvls(const SyncParams& p, int grid, cudaStream_t stream);
+// Elements per receive slot of the push kernel for (count, world).
+uint64_t push_recv_stride(uint64_t count, int world);
 // Occupancy-derived default grid (co-resident CTAs) for the vector kernel.
 int default_sync_grid(int device);
 // Device-side synthetic fill, identical to cos_oracle_fill (tests/bench).

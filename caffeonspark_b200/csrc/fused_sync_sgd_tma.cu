@@ -78,6 +78,10 @@ __device__ __forceinline__ void tma_wait_read() {
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // make generic-proxy writes to shared memory visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// order generic-proxy accesses to GLOBAL memory (the bf16 wire cast of phase 0, the peers' gradients acquired
+// through the generic-proxy flag loads of barrier A) against the async-proxy bulk copies that follow, and the
+// completed bulk stores against the generic-proxy release of barrier B (PTX memory model: cross-proxy fence)
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ------------------------------------------------------------- job iterator
 
@@ -266,6 +270,7 @@ fused_sync_sgd_tma_kernel(const SyncParams p, const int tile_elems) {
   cons.init(p, tile_elems, A);
   prod = cons;
   if (tid == 0) {  // prologue: kStages-1 tiles in flight
+    fence_async_all();
     for (int k = 0; k < kStages - 1 && prod.valid; ++k) {
       issue_loads(prod, k);
       prod.next(p);
@@ -354,7 +359,10 @@ fused_sync_sgd_tma_kernel(const SyncParams p, const int tile_elems) {
       }
     }
   }
-  if (tid == 0) tma_wait_all();  // every weight / history tile has landed (incl. peer memory)
+  if (tid == 0) {
+    tma_wait_all();  // every weight / history tile has landed (incl. peer memory)
+    fence_async_all();
+  }
 
   // scalar head / tail of each range (<= 3 elements each), plain loads/stores by CTA 0
   if (blockIdx.x == 0) {

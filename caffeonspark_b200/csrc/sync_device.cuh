@@ -82,24 +82,35 @@ __device__ __forceinline__ uint32_t* flag_slot(uint32_t* base, int which, int ct
   return base + (static_cast<size_t>(which) * kMaxCtas + cta) * kMaxRanks + src;
 }
 
-// Barrier between CTA blockIdx.x of every rank.  Thread t < world handles peer
-// t: it publishes this launch's epoch into the peer's flag slot [cta][rank]
-// and spins on the local slot [cta][t].  Flags are only ever polled in LOCAL
-// memory (peers store into it), so spinning costs no NVLink bandwidth.
-// The leading __syncthreads + system fence make every store of the CTA (e.g.
-// weight pushes into peer memory) visible before the flag is.
-// Returns false if a peer did not arrive within timeout_ns (status is set).
-__device__ bool cta_barrier(const SyncParams& p, int which, int* s_abort) {
+// Barrier between CTA blockIdx.x of every rank, split into its two halves.
+// Thread t < world handles peer t.  cta_signal publishes this launch's epoch
+// into the peer's flag slot [cta][rank]: the leading __syncthreads orders every
+// store of the CTA (e.g. pushes into peer memory) before the releasing thread,
+// and st.release.sys (= fence.acq_rel.sys + store, cumulative over the bar.sync)
+// makes them visible before the flag is.  cta_wait spins on the LOCAL slot
+// [cta][t] (peers store into it, so spinning costs no NVLink bandwidth) with
+// relaxed loads and issues ONE acquire fence after the flag arrived.
+// cta_wait returns false if a peer did not arrive within timeout_ns (status is set).
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void cta_signal(const SyncParams& p, int which) {
   __syncthreads();
   const int t = threadIdx.x;
+  if (t < p.world && t != p.rank) st_release_sys(flag_slot(p.flags[t], which, blockIdx.x, p.rank), p.epoch);
+}
+
+__device__ __forceinline__ bool cta_wait(const SyncParams& p, int which, int* s_abort) {
+  const int t = threadIdx.x;
   if (t < p.world && t != p.rank) {
-    __threadfence_system();
-    st_release_sys(flag_slot(p.flags[t], which, blockIdx.x, p.rank), p.epoch);
     const uint32_t* mine = flag_slot(p.flags[p.rank], which, blockIdx.x, t);
     const unsigned long long t0 = globaltimer_ns();
     unsigned spins = 0;
     for (;;) {
-      uint32_t v = ld_acquire_sys(mine);
+      uint32_t v = ld_relaxed_sys(mine);
       if (static_cast<int32_t>(v - p.epoch) >= 0) break;
       if ((++spins & 0x3ffu) == 0) {
         if (*reinterpret_cast<volatile int*>(s_abort)) break;
@@ -110,9 +121,15 @@ __device__ bool cta_barrier(const SyncParams& p, int which, int* s_abort) {
         }
       }
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");  // acquire: later loads see what the peer released
   }
   __syncthreads();
   return *reinterpret_cast<volatile int*>(s_abort) == 0;
+}
+
+__device__ __forceinline__ bool cta_barrier(const SyncParams& p, int which, int* s_abort) {
+  cta_signal(p, which);
+  return cta_wait(p, which, s_abort);
 }
 
 // ------------------------------------------------------------- partition

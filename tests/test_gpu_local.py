@@ -121,7 +121,7 @@ def test_full_size_caffenet_properties(cos, oracle, kernel):
     desc = nets.solver_desc("caffenet")
     assert desc.param_count == 60965224
     sim = oracle.Simulation(1, desc.counts, desc.lr_mult, desc.decay_mult, seed=5, **desc.hyper())
-    R = Ranks(cos, desc, 1, kernel=kernel)
+    R = Ranks(cos, desc, 1, kernel=kernel, timing=1)
     try:
         R.set_weights([sim.data[0]])
         R.connect()

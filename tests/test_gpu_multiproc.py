@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0, nvls=False):
+def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0, nvls=False, opts=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     dev = 0 if shared_gpu else rank
@@ -51,6 +51,8 @@ def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0, nvls=F
         net.set_option("algo", algo)
         net.set_option("kernel", kernel)
         net.set_option("nvls", int(nvls))
+        for k, v in (opts or {}).items():
+            net.set_option(k, v)
         net.set_option("barrier_timeout_ms", 60000 if shared_gpu else 15000)
         if shared_gpu:  # contexts time-slice on the one GPU: keep the spinning grids tiny
             net.set_option("grid", 2)
@@ -86,7 +88,7 @@ def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0, nvls=F
 
 @pytest.mark.skipif(gpu_count() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("algo,bf16,kernel", [(1, False, 0), (2, False, 0), (1, True, 0), (1, False, 1), (2, False, 1),
-                                              (1, True, 1)])
+                                              (1, True, 1), (1, False, 2), (1, True, 2)])
 def test_one_process_per_gpu_bit_exact(cos, oracle, algo, bf16, kernel):
     import torch.multiprocessing as mp
     world = min(gpu_count(), 8)
@@ -105,17 +107,21 @@ def test_one_process_per_gpu_bit_exact(cos, oracle, algo, bf16, kernel):
 
 
 @pytest.mark.skipif(gpu_count() < 2, reason="needs >= 2 GPUs")
-def test_nvls_two_shot_within_tolerance(cos, oracle):
-    """NVLS variant (multimem.ld_reduce / multimem.st through the NVSwitch): the
-    in-switch summation order is unspecified, so the bar is the north star's
-    1e-5 relative.  If the platform does not expose multicast the library keeps
-    the P2P path (then the result must be bit-exact) -- reported, not failed."""
+@pytest.mark.parametrize("unroll,p2p", [(4, 0), (8, 0), (1, 0), (2, 1), (4, 1)])
+def test_nvls_two_shot_within_tolerance(cos, oracle, unroll, p2p):
+    """NVLS kernel (multimem.ld_reduce / multimem.st through the NVSwitch, optionally sharing the work with
+    plain P2P vectors): the in-switch summation order is unspecified, so the bar is the north star's 1e-5
+    relative.  If the platform does not expose multicast the library keeps the P2P path (then the result must
+    be bit-exact) -- reported, not failed.  The P2P share exists for world sizes 2, 4 and 8."""
     import torch.multiprocessing as mp
     world = min(gpu_count(), 8)
+    if p2p and world not in (2, 4, 8):
+        world = 4 if world > 4 else 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 1, False, q, False, 0, True)) for r in range(world)]
+    opts = {"nvls_unroll": unroll, "nvls_p2p": p2p}
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 1, False, q, False, 3, True, opts)) for r in range(world)]
     [p.start() for p in procs]
     [p.join(300) for p in procs]
     for p in procs:
@@ -131,7 +137,8 @@ def test_nvls_two_shot_within_tolerance(cos, oracle):
 
 @pytest.mark.skipif(gpu_count() < 1, reason="needs a GPU")
 @pytest.mark.parametrize("world,algo,bf16,kernel", [(2, 1, False, 0), (3, 2, False, 1), (5, 1, True, 0),
-                                                    (8, 1, False, 1), (8, 2, False, 0)])
+                                                    (8, 1, False, 1), (8, 2, False, 0), (5, 1, False, 2),
+                                                    (8, 1, True, 2)])
 def test_processes_sharing_one_gpu_bit_exact(cos, oracle, world, algo, bf16, kernel):
     """Several executor PROCESSES on the single test GPU: the cross-process
     descriptor-passing / VMM import path and the device-side barriers between
