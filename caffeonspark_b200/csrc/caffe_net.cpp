@@ -90,8 +90,15 @@ CaffeNet::~CaffeNet() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
     cudaDeviceSynchronize();
-    for (void* p : in_dev_)
-      if (p) cudaFree(p);
+    for (InputStage& st : stage_) {
+      for (void* p : st.dev)
+        if (p) cudaFree(p);
+      if (st.copied) cudaEventDestroy(st.copied);
+      if (st.consumed) cudaEventDestroy(st.consumed);
+    }
+    for (cudaEvent_t e : loss_ev_)
+      if (e) cudaEventDestroy(e);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     if (seg_end_) cudaFree(seg_end_);
     if (seg_lr_) cudaFree(seg_lr_);
     if (seg_dm_) cudaFree(seg_dm_);
@@ -208,9 +215,15 @@ bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::str
   memset(status_, 0, 16 * sizeof(unsigned long long));
   COS_RT(cudaMalloc(reinterpret_cast<void**>(&loss_dev_), sizeof(float)));
   COS_RT(cudaMemset(loss_dev_, 0, sizeof(float)));
-  COS_RT(cudaHostAlloc(reinterpret_cast<void**>(&loss_host_), sizeof(float), cudaHostAllocDefault));
-  *loss_host_ = 0.f;
+  COS_RT(cudaHostAlloc(reinterpret_cast<void**>(&loss_host_), 2 * sizeof(float), cudaHostAllocDefault));
+  loss_host_[0] = loss_host_[1] = 0.f;
   COS_RT(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  COS_RT(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  for (InputStage& st : stage_) {
+    COS_RT(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming));
+    COS_RT(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming));
+  }
+  for (cudaEvent_t& e : loss_ev_) COS_RT(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   COS_RT(cudaEventCreate(&ev_start_));
   COS_RT(cudaEventCreate(&ev_stop_));
   COS_RT(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
@@ -402,6 +415,7 @@ bool CaffeNet::synchronize(std::string* err) {
   COS_RT(cudaSetDevice(device_));
   if (done_valid_) COS_RT(cudaEventSynchronize(ev_done_));
   COS_RT(cudaStreamSynchronize(stream_));
+  harvest_losses(true);
   return check_status(err);
 }
 
@@ -436,11 +450,15 @@ bool CaffeNet::train(int solver_index, const cos_blob* data, int ndata, std::str
     return false;
   }
   COS_RT(cudaSetDevice(device_));
-  // MemoryInputAdapter::feed (MemoryInputAdapter.cpp:24-32) equivalent: stage host blobs on the device
-  if (static_cast<int>(in_dev_.size()) < ndata) {
-    in_dev_.resize(ndata, nullptr);
-    in_bytes_.resize(ndata, 0);
+  if (!check_status(err)) return false;  // a device-side error of an earlier (pipelined) step surfaces here
+  // MemoryInputAdapter::feed (MemoryInputAdapter.cpp:24-32) equivalent: stage the host blobs on the device.
+  // Stage k was last read by step t-2: its H2D may only start once that step is done (device-side wait).
+  InputStage& st = stage_[stage_idx_];
+  if (static_cast<int>(st.dev.size()) < ndata) {
+    st.dev.resize(ndata, nullptr);
+    st.bytes.resize(ndata, 0);
   }
+  if (st.consumed_valid) COS_RT(cudaStreamWaitEvent(copy_stream_, st.consumed, 0));
   std::vector<cos_blob> dev_blobs(ndata);
   for (int i = 0; i < ndata; ++i) {
     if (!data[i].data) {
@@ -448,26 +466,63 @@ bool CaffeNet::train(int solver_index, const cos_blob* data, int ndata, std::str
       return false;
     }
     size_t n = static_cast<size_t>(data[i].num) * data[i].channels * data[i].height * data[i].width * sizeof(float);
-    if (n > in_bytes_[i]) {
-      if (in_dev_[i]) cudaFree(in_dev_[i]);
-      in_dev_[i] = nullptr;
-      COS_RT(cudaMalloc(&in_dev_[i], n));
-      in_bytes_[i] = n;
+    if (n > st.bytes[i]) {
+      if (st.dev[i]) {
+        COS_RT(cudaStreamSynchronize(stream_));  // an earlier step may still read the old buffer
+        cudaFree(st.dev[i]);
+      }
+      st.dev[i] = nullptr;
+      COS_RT(cudaMalloc(&st.dev[i], n));
+      st.bytes[i] = n;
     }
-    COS_RT(cudaMemcpyAsync(in_dev_[i], data[i].data, n, cudaMemcpyHostToDevice, stream_));
+    COS_RT(cudaMemcpyAsync(st.dev[i], data[i].data, n, cudaMemcpyHostToDevice, copy_stream_));
     dev_blobs[i] = data[i];
-    dev_blobs[i].data = static_cast<const float*>(in_dev_[i]);
+    dev_blobs[i].data = static_cast<const float*>(st.dev[i]);
   }
+  COS_RT(cudaEventRecord(st.copied, copy_stream_));
+  COS_RT(cudaStreamWaitEvent(stream_, st.copied, 0));
   int rc = fb_fn_(fb_user_, solver_index_, dev_blobs.data(), ndata, loss_dev_, stream_);
   if (rc != 0) {
     *err = "gradient producer failed with code " + std::to_string(rc);
     return false;
   }
   if (!sync_step(solver_index, stream_, true, err)) return false;
-  COS_RT(cudaMemcpyAsync(loss_host_, loss_dev_, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+  COS_RT(cudaEventRecord(st.consumed, stream_));
+  st.consumed_valid = true;
+  // the step's result (loss): device -> pinned host on the compute stream, harvested when it has arrived
+  const int k = loss_idx_;
+  if (loss_pending_[k]) COS_RT(cudaEventSynchronize(loss_ev_[k]));
+  harvest_losses(false);
+  COS_RT(cudaMemcpyAsync(loss_host_ + k, loss_dev_, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+  COS_RT(cudaEventRecord(loss_ev_[k], stream_));
+  loss_pending_[k] = true;
+  loss_idx_ ^= 1;
+  stage_idx_ ^= 1;
+  if (opt_train_pipeline_) {
+    // the caller owns the host blobs again once train() returns: wait for THIS batch's H2D only
+    COS_RT(cudaEventSynchronize(st.copied));
+    harvest_losses(false);
+    return true;
+  }
   COS_RT(cudaStreamSynchronize(stream_));
-  last_loss_ = *loss_host_;
+  harvest_losses(true);
   return check_status(err);
+}
+
+// Collects the losses whose D2H has completed (oldest first, so last_loss_ ends at the newest one).
+void CaffeNet::harvest_losses(bool wait) {
+  for (int n = 0; n < 2; ++n) {
+    const int k = (loss_idx_ + n) & 1;  // loss_idx_ is the OLDER slot
+    if (!loss_pending_[k]) continue;
+    cudaError_t e = wait ? cudaEventSynchronize(loss_ev_[k]) : cudaEventQuery(loss_ev_[k]);
+    if (e == cudaSuccess) {
+      last_loss_ = loss_host_[k];
+      loss_pending_[k] = false;
+    } else {
+      cudaGetLastError();
+      if (!wait) break;  // the newer one cannot be done either
+    }
+  }
 }
 
 bool CaffeNet::set_option(const std::string& name, int64_t v, std::string* err) {
@@ -491,6 +546,7 @@ bool CaffeNet::set_option(const std::string& name, int64_t v, std::string* err) 
   else if (name == "initial_gather") opt_initial_gather_ = v != 0;
   else if (name == "trace") opt_trace_ = v != 0;
   else if (name == "small_grid") opt_small_grid_ = v != 0;
+  else if (name == "train_pipeline") opt_train_pipeline_ = v != 0;
   else {
     *err = "unknown option '" + name + "'";
     return false;
@@ -518,6 +574,7 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "one_shot_max_bytes") return opt_one_shot_max_bytes_;
   if (name == "initial_gather") return opt_initial_gather_;
   if (name == "small_grid") return opt_small_grid_;
+  if (name == "train_pipeline") return opt_train_pipeline_;
   if (name.compare(0, 6, "trace_") == 0 && name.size() == 7 && name[6] >= '0' && name[6] <= '4')
     return static_cast<int64_t>((reinterpret_cast<volatile unsigned long long*>(status_) + 2)[name[6] - '0']);
   if (name == "transport") return arena_.transport();

@@ -51,7 +51,7 @@ class CaffeNet {
   std::string snapshot_filename(int iter, bool is_state) const;  // Solver::SnapshotFilename
   std::vector<BlobView> blob_views(const float* flat) const;
   // resume from snapshot files, ours or stock Caffe's (CaffeNet.cpp:198-205 restore path)
-  bool restore(const std::string& model_file, const std::string& state_file, std::string* err);
+  virtual bool restore(const std::string& model_file, const std::string& state_file, std::string* err);
   int getInitIter(int solver_index) const { return solver_index == 0 ? spec_.init_iter : -1; }
   int getMaxIter(int solver_index) const { return solver_index == 0 ? spec_.max_iter : -1; }
   int getTestIter(int solver_index) const { return solver_index == 0 ? spec_.test_iter : -1; }
@@ -158,8 +158,26 @@ class CaffeNet {
   cos_forward_backward_fn fb_fn_ = nullptr;
   void* fb_user_ = nullptr;
   int solver_index_ = 0;  // index the gradient producer sees (local device number inside the executor)
-  std::vector<void*> in_dev_;       // staged input blobs
-  std::vector<size_t> in_bytes_;
+  // Input path (row f3): the reference keeps a 2-deep Free/Full queue of host blobs between the transformer
+  // threads and the solver thread (CaffeProcessor.scala:32-35,442-452) and MemoryInputAdapter::feed points the
+  // data layer at the host blob (MemoryInputAdapter.cpp:24-32).  Here: two device-side staging sets; the H2D
+  // copy of batch t runs on its own copy stream while the compute stream still works on batch t-1; train()
+  // returns as soon as ITS batch has left host memory (the caller recycles the blobs after train() returns).
+  struct InputStage {
+    std::vector<void*> dev;
+    std::vector<size_t> bytes;
+    cudaEvent_t copied = nullptr;    // H2D of this stage finished
+    cudaEvent_t consumed = nullptr;  // the step that read this stage finished
+    bool consumed_valid = false;
+  };
+  InputStage stage_[2];
+  int stage_idx_ = 0;
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t loss_ev_[2] = {nullptr, nullptr};
+  bool loss_pending_[2] = {false, false};
+  int loss_idx_ = 0;
+  int opt_train_pipeline_ = 1;      // 0: train() returns only after the whole Step finished (reference behaviour)
+  void harvest_losses(bool wait);
   std::vector<std::string> addr_store_;
   std::vector<const char*> addr_cstrs_;
   std::mutex mu_;
@@ -212,6 +230,13 @@ class MultiDeviceCaffeNet : public CaffeNet {
   }
   int num_local_devices() const override { return static_cast<int>(ranks_.size()); }
   int snapshot(std::string* err) override { return ranks_[0]->snapshot(err); }
+  // every local solver restores the same files (CaffeNet.cpp:196-205 runs per solver): weights, history,
+  // iter_ and current_step_ on each local rank
+  bool restore(const std::string& model_file, const std::string& state_file, std::string* err) override {
+    for (auto& r : ranks_)
+      if (!r->restore(model_file, state_file, err)) return false;
+    return true;
+  }
   bool synchronize(std::string* err) override;
   void set_forward_backward(cos_forward_backward_fn fn, void* user) override;
   int64_t launch_count() const override;

@@ -33,6 +33,7 @@ def test_train_lenet_from_prototxt(cos, oracle, tmp_path):
             torch.cuda.synchronize()
             rate = net.learning_rate()
             assert net.train(0, [x, y]), net.last_error()
+            assert net.synchronize(), net.last_error()  # train() is pipelined: it returns once the batch left host memory
             losses.append(net.last_loss())
             g = to_host(net.diff())  # the gradient the producer accumulated (diff_ not cleared)
             oracle.apply_update(0, desc.param_count, w_before, g.copy(), h_before, desc.counts, desc.lr_mult,
@@ -76,7 +77,9 @@ def test_train_two_ranks_in_process(cos, oracle):
             out = []
             for _ in range(6):
                 assert netz[r].train(0, list(batches[r])), netz[r].last_error()
-                out.append(netz[r].last_loss())
+                out.append(netz[r].last_loss())  # pipelined: the newest loss that has ARRIVED (may lag a step)
+            assert netz[r].synchronize(), netz[r].last_error()
+            out.append(netz[r].last_loss())
             return out
 
         with cf.ThreadPoolExecutor(2) as ex:
@@ -89,3 +92,39 @@ def test_train_two_ranks_in_process(cos, oracle):
     finally:
         with cf.ThreadPoolExecutor(2) as ex:
             list(ex.map(lambda n: n.deallocate(), netz))
+
+
+def test_train_pipelined_equals_synchronous(cos, oracle):
+    """Row f3: train() double-buffers the input staging (H2D of batch t+1 on a copy stream while step t
+    computes) and returns once its batch has left host memory.  The caller may then overwrite the host blobs
+    (the Scala side recycles them, CaffeProcessor.scala:442-452): do exactly that, and require the run to be
+    bit-identical to the fully synchronous one (train_pipeline=0) on the same batch sequence."""
+    from caffeonspark_b200 import harness, nets
+    desc = nets.solver_desc("lenet")
+    rng = np.random.RandomState(3)
+    xs = [rng.rand(64, 1, 28, 28).astype(np.float32) for _ in range(8)]
+    ys = [rng.randint(0, 10, (64, 1, 1, 1)).astype(np.float32) for _ in range(8)]
+    results = []
+    for pipeline in (0, 1):
+        net = cos.CaffeNet(desc)
+        try:
+            assert net.connect(net.localAddresses())
+            net.set_option("train_pipeline", pipeline)
+            harness.make_producer("lenet", net, seed=11)
+            x, y = torch.empty(64, 1, 28, 28).pin_memory(), torch.empty(64, 1, 1, 1).pin_memory()
+            losses = []
+            for t in range(8):
+                x.copy_(torch.from_numpy(xs[t]))  # ONE pair of host blobs, overwritten right after train() returns
+                y.copy_(torch.from_numpy(ys[t]))
+                assert net.train(0, [x, y]), net.last_error()
+                x.fill_(float("nan"))             # a late H2D would poison the run
+            assert net.synchronize(), net.last_error()
+            losses.append(net.last_loss())
+            assert net.iter() == 8
+            results.append((to_host(net.data()), to_host(net.history()), losses[-1]))
+        finally:
+            net.deallocate()
+    assert np.isfinite(results[0][0]).all()
+    assert_bits_equal(results[1][0], results[0][0], "pipelined vs synchronous weights")
+    assert_bits_equal(results[1][1], results[0][1], "pipelined vs synchronous history")
+    assert results[0][2] == results[1][2]
