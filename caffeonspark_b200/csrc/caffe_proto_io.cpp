@@ -255,7 +255,10 @@ bool read_caffemodel(const std::string& path, std::string* net_name, std::vector
           lr.skip(wt2);
         }
       }
-      if (!lr.ok) break;
+      if (!lr.ok) {  // a truncated / malformed LayerParameter must not yield a silently partial layer list
+        *err = "'" + path + "': malformed LayerParameter" + (L.name.empty() ? std::string() : " '" + L.name + "'");
+        return false;
+      }
       layers->push_back(std::move(L));
     } else {
       if (f == 2 && wt == kLen) saw_v1 = true;  // V1LayerParameter layers

@@ -252,6 +252,22 @@ void PeerAdapter::listen_loop() {
 // pthread per peer).  Requests are answered on the same connection.
 void PeerAdapter::serve(int fd) {
   int src = -1;
+  // The rendezvous name is discoverable (/proc/net/unix) and a fetch hands out a read/write handle of the GPU
+  // arena: only serve peers running under our own effective uid (or root).  COS_ALLOW_ANY_UID=1 lifts this for
+  // executors whose containers map uids differently.
+  {
+    struct ucred cred;
+    socklen_t len = sizeof(cred);
+    const bool known = getsockopt(fd, SOL_SOCKET, SO_PEERCRED, &cred, &len) == 0 && len == sizeof(cred);
+    if (!getenv("COS_ALLOW_ANY_UID") && (!known || (cred.uid != geteuid() && cred.uid != 0))) {
+      shutdown(fd, SHUT_RDWR);
+      close(fd);
+      std::lock_guard<std::mutex> g(mu_);
+      for (int& f : server_fds_)
+        if (f == fd) f = -1;
+      return;
+    }
+  }
   for (;;) {
     Header h;
     std::string payload;
@@ -280,11 +296,16 @@ void PeerAdapter::serve(int fd) {
         found = cv_.wait_for(g, std::chrono::milliseconds(timeout_ms),
                              [&] { return stop_ || offers_.count(key) > 0; }) &&
                 offers_.count(key) > 0;
-        if (found) o = offers_[key];
+        if (found) {
+          o = offers_[key];
+          if (o.fd >= 0) o.fd = dup(o.fd);  // our own copy, taken under the lock: offer() may close the original
+        }
       }
       std::string reply(1, found ? (o.fd >= 0 ? 'F' : 'M') : 'N');
       reply += o.meta;
-      if (!send_msg(fd, kFetchReply, rank_, reply, found ? o.fd : -1)) break;
+      const bool sent = send_msg(fd, kFetchReply, rank_, reply, found ? o.fd : -1);
+      if (o.fd >= 0) close(o.fd);
+      if (!sent) break;
     } else {
       break;
     }

@@ -3,7 +3,9 @@
 
 #include <cuda.h>
 #include <cuda_runtime_api.h>
+#include <stdio.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <mutex>
@@ -259,10 +261,29 @@ void DeviceArena::destroy() {
   vmm_ = false;
 }
 
+uint64_t process_nonce() {
+  static const uint64_t nonce = [] {
+    uint64_t v = 0;
+    if (FILE* f = fopen("/dev/urandom", "rb")) {
+      if (fread(&v, sizeof(v), 1, f) != 1) v = 0;
+      fclose(f);
+    }
+    if (v == 0) {
+      struct timespec ts;
+      clock_gettime(CLOCK_REALTIME, &ts);
+      v = (static_cast<uint64_t>(getpid()) << 40) ^ (static_cast<uint64_t>(ts.tv_sec) << 20) ^
+          static_cast<uint64_t>(ts.tv_nsec) ^ reinterpret_cast<uint64_t>(&v);
+    }
+    return v | 1;  // never 0
+  }();
+  return nonce;
+}
+
 ArenaMeta DeviceArena::meta() const {
   ArenaMeta m;
   memset(&m, 0, sizeof(m));
-  m.version = 1;
+  m.version = 2;
+  m.proc_nonce = process_nonce();
   m.transport = transport_;
   m.pid = static_cast<int64_t>(getpid());
   m.device = device_;
@@ -304,7 +325,7 @@ PeerMapping::~PeerMapping() { close(); }
 
 bool PeerMapping::open(const ArenaMeta& m, int fd, int my_device, std::string* err) {
   close();
-  if (m.version != 1) {
+  if (m.version != 2) {
     if (fd >= 0) ::close(fd);
     *err = "peer arena metadata version mismatch";
     return false;
@@ -315,7 +336,7 @@ bool PeerMapping::open(const ArenaMeta& m, int fd, int my_device, std::string* e
     *err = rt_err("cudaSetDevice", e);
     return false;
   }
-  if (m.pid == static_cast<int64_t>(getpid())) {
+  if (m.proc_nonce == process_nonce()) {  // NOT the raw pid: pids collide across PID namespaces
     // in-process rank: same address space (the owner grants access if needed)
     if (fd >= 0) ::close(fd);
     if (m.device != my_device) {  // another GPU of this process: open the access path from here

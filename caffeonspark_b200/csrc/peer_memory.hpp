@@ -32,9 +32,16 @@ struct ArenaMeta {
   int32_t device;
   int32_t reserved;
   uint64_t bytes;
-  uint64_t base_ptr;  // valid inside process `pid` only
+  uint64_t base_ptr;  // valid inside the process identified by (pid, proc_nonce) only
+  // Random per-process token (process_nonce()).  PIDs collide across PID namespaces (executors in separate
+  // containers reached through COS_SOCKET_DIR often all run as PID 1), so "same process" is decided by the
+  // nonce; the pid is kept for diagnostics.
+  uint64_t proc_nonce;
   unsigned char ipc_handle[64];
 };
+
+// 64 random bits drawn once per process (from /dev/urandom; falls back to pid, clock and an address).
+uint64_t process_nonce();
 
 class DeviceArena {
  public:

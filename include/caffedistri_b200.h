@@ -155,8 +155,10 @@ COS_API int cos_net_get_test_interval(cos_net* net);
 
 /* J:171 snapshot / JN:537-548, CN:735-738 -> Solver::Snapshot (solver.cpp:400-425):
  * writes stock-Caffe binaryproto files <prefix>_iter_<n>.caffemodel (NetParameter)
- * and .solverstate (SolverState; ".h5" appended to the NAMES for snapshot_format
- * HDF5) and returns the iteration, -1 on failure.  Called on rank 0 only, like
+ * and .solverstate (SolverState) and returns the iteration, -1 on failure.  A solver
+ * asking for snapshot_format: HDF5 (sgd_solver.cpp:279-323) trains normally but its
+ * snapshot() fails with a clear error: there is no HDF5 writer here, and binaryproto
+ * content under ".h5" names would break every stock reader.  Called on rank 0 only, like
  * the reference (CaffeProcessor.scala:454-465); NOT collective: the history
  * shards of the other ranks are read through their mapped arenas. */
 COS_API int cos_net_snapshot(cos_net* net);

@@ -171,3 +171,24 @@ def test_garbage_is_rejected(cos, tmp_path):
     assert L.cos_caffemodel_read(str(p).encode(), b"x", 0, None, 0) == -1
     assert L.cos_solverstate_read(str(p).encode(), None, None, None, 0, -1, None, 0) == -1
     assert L.cos_caffemodel_read(str(tmp_path / "missing").encode(), b"x", 0, None, 0) == -1
+
+
+def test_malformed_layer_is_an_error_not_a_partial_model(cos, pb, tmp_path):
+    """A LayerParameter whose body is cut short must fail the whole read: returning the layers parsed so far would
+    let a resume silently keep random weights for the rest (Net::CopyTrainedLayersFrom would have CHECK-failed)."""
+    from caffeonspark_b200 import _lib
+    L = _lib.lib()
+    net = pb["NetParameter"](name="n")
+    a = net.layer.add(name="a", type="InnerProduct")
+    b = a.blobs.add()
+    b.shape.dim.extend([2, 2])
+    b.data.extend([1.0, 2.0, 3.0, 4.0])
+    good = net.SerializeToString()
+    bad_layer = b"\x0a\x01b" + b"\x12\x7f"  # name "b", then field 2 (type) announcing 127 bytes that are not there
+    blob = good + b"\xa2\x06" + bytes([len(bad_layer)]) + bad_layer + good[2 + len("n"):]  # a, broken b, a again
+    p = tmp_path / "broken.caffemodel"
+    p.write_bytes(blob)
+    assert L.cos_caffemodel_read(str(p).encode(), b"a", 0, None, 0) == -1
+    assert b"malformed LayerParameter" in L.cos_last_error()
+    p.write_bytes(good)
+    assert L.cos_caffemodel_read(str(p).encode(), b"a", 0, None, 0) == 4

@@ -206,3 +206,23 @@ def test_snapshot_restore_resumes_bit_exactly(cos, oracle, tmp_path):
         assert_bits_equal(to_host(c.data()), w_at_2, "copyLayers restores the weights")
     finally:
         c.deallocate()
+
+
+def test_hdf5_snapshot_format_trains_but_refuses_to_snapshot(cos, tmp_path):
+    """The reference's own cifar10_quick_solver.prototxt asks for snapshot_format: HDF5.  Such a solver must
+    load and train; snapshot() must fail loudly (no HDF5 writer here) instead of writing binaryproto content
+    under the .h5 names CaffeNet.java:203-205 computes."""
+    from caffeonspark_b200 import nets
+    (tmp_path / "net.prototxt").write_text(nets.net_prototxt("cifar10_quick"))
+    (tmp_path / "solver.prototxt").write_text(
+        f'net: "net.prototxt"\nbase_lr: 0.001\nmomentum: 0.9\nweight_decay: 0.004\nlr_policy: "fixed"\n'
+        f'max_iter: 10\nsnapshot_format: HDF5\nsnapshot_prefix: "{tmp_path / "c10"}"\n')
+    net = cos.CaffeNet(str(tmp_path / "solver.prototxt"))
+    try:
+        assert net.connect(net.localAddresses())
+        assert net.sync_step(0) and net.synchronize()
+        assert net.snapshotFilename(1, False).endswith("_iter_1.caffemodel.h5")
+        assert net.snapshot() == -1 and "HDF5 is not supported" in net.last_error()
+        assert not list(tmp_path.glob("c10_iter_*"))
+    finally:
+        net.deallocate()
