@@ -121,7 +121,7 @@ def cuda_time_steps(torch, dist, world, steps, warmup, step_fn, flush_fn):
     return total
 
 
-def algorithmic_bytes(P, world, mode, zero_diff, bf16):
+def algorithmic_bytes(P, world, mode, zero_diff, bf16, nvls=False, push=False):
     """DESIGN.md section 'algorithmic bytes': per launch, per GPU.
     -> (hbm_bytes, nvlink_bytes_per_direction)"""
     z = 4 * P if zero_diff else 0
@@ -129,33 +129,146 @@ def algorithmic_bytes(P, world, mode, zero_diff, bf16):
         return 20 * P + z, 0                      # read g,w,h ; write w,h (+ zero g)
     bg = 2 if bf16 else 4
     f = (world - 1) / world
-    cast = (4 * P + 2 * P) if bf16 else 0         # phase 0: read fp32, write bf16 wire
+    if nvls:                                      # switch reads every rank once, owner multicasts its shard
+        hbm = 4 * P + 4 * P + 12 * P / world + z  # serve the switch's reads, land the multicast, own w/h
+        return hbm, 4 * P * (1 + 1 / world)       # up: 4P served + 4P/N stored; down: 4P/N reduced + 4P landed
+    if push:                                      # cast in registers: no wire buffer; slots written + read once
+        hbm = 4 * P + 2 * bg * P * f + 4 * P * f + 16 * P / world + z
+        return hbm, (bg + 4) * P * f
+    cast = (4 * P + 2 * P) if bf16 else 0         # pull kernels, phase 0: read fp32, write bf16 wire
     if mode == 2:                                 # one-shot: read all peers' full gradient, update everything
         return cast + bg * P + 20 * P + z, bg * P * (world - 1)
     hbm = cast + bg * P + 4 * P * f + 12 * P / world + 4 * P / world + z  # serve grads, land pushes, own shard
     return hbm, (bg + 4) * P * f                  # pull grads + push weights
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import caffeonspark_b200 as C
-    from caffeonspark_b200 import harness, nets
+class NvlinkCounters:
+    """NVML per-GPU NVLink data counters (KiB, summed over the links): payload bytes that really crossed the
+    links, read before/after K launches -- evidence that is not events / formula."""
+    IDS = {"data_tx": 138, "data_rx": 139, "raw_tx": 140, "raw_rx": 141}  # NVML_FI_DEV_NVLINK_THROUGHPUT_*
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
-    torch.cuda.set_device(local)
+    def __init__(self, torch, device):
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception as e:  # no NVML / no NVLink: the caller reports traffic as unavailable
+            self.err = repr(e)
+
+    def read(self):
+        if self.h is None:
+            return None
+        try:
+            vals = self.nv.nvmlDeviceGetFieldValues(self.h, [(i, 0xFFFFFFFF) for i in self.IDS.values()])
+            out = {}
+            for k, v in zip(self.IDS, vals):
+                if v.nvmlReturn != 0:
+                    return None
+                out[k] = int(v.value.ullVal) * 1024
+            return out
+        except Exception:
+            return None
+
+
+def measure_nvlink_traffic(torch, dist, net, world, launches=50):
+    """NVLink payload bytes per fused-kernel launch on this rank's GPU (NVML counters around `launches`
+    back-to-back launches; the counters tick in KiB, so many launches are needed for small nets)."""
+    ctr = NvlinkCounters(torch, torch.cuda.current_device())
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.backends.cudnn.benchmark = not os.environ.get("COS_BENCH_NO_AUTOTUNE")  # off under ncu launch lists
-    torch.backends.cuda.matmul.allow_tf32 = True
-    torch.backends.cudnn.allow_tf32 = True
+        dist.barrier()
+    c0 = ctr.read()
+    with torch.cuda.stream(st):
+        for _ in range(launches):
+            if not net.sync_step(0, st.cuda_stream):
+                raise RuntimeError(net.last_error())
+    torch.cuda.synchronize()
+    if not net.synchronize():
+        raise RuntimeError(net.last_error())
+    if world > 1:
+        dist.barrier()
+    time.sleep(0.05)
+    c1 = ctr.read()
+    if c0 is None or c1 is None:
+        return None
+    return {k: (c1[k] - c0[k]) / launches for k in c0}
 
-    name = args.workload
-    bf16 = args.grad_dtype == "bf16"
-    desc = nets.solver_desc(name, grad_dtype=args.grad_dtype)
+
+def parity_check(torch, dist, C, harness, desc, name, rank, world, local, args, kernels):
+    """Outside every timed region: two seeded steps on fresh nets, on ALL ranks, compared with the CPU oracle on
+    rank 0 (this is the `cpu_baseline` leg, the one place bench.py may use oracle/).  Weights / gradients come
+    from the device-side generator that is bit-identical to cos_oracle_fill.  Every rank must hold identical
+    bits; rank 0's full weights and own history shard are compared with oracle.Simulation element by element
+    (bit-exact for the P2P kernels; the NVLS kernel is held to the north star's 1e-5 relative)."""
+    import numpy as np
+    seed, res = 20260921, {}
+    expected = None
+    for kern in kernels:
+        cl = harness.Cluster(desc, rank=rank, world=world, device=local)
+        net = cl.net
+        net.set_option("kernel", kern)
+        net.set_option("nvls", int(args.nvls) if kern in (-1, 3) else 0)
+        net.set_option("barrier_timeout_ms", 120000)
+        net.fill("data", seed, 0, 0.05)
+        torch.cuda.synchronize()
+        cl.start()
+        for t in range(2):
+            net.fill("diff", seed, (t + 1) * 4096 + rank, 0.01)
+            if not (net.sync_step(0) and net.synchronize()):
+                raise RuntimeError(net.last_error())
+        w = net.data()
+        o, n = net.shard()
+        sums = torch.stack([w.view(torch.int32).to(torch.int64).sum(), (w.view(torch.int32).to(torch.int64) *
+                            torch.arange(1, w.numel() + 1, device=w.device, dtype=torch.int64) % 1000003).sum()])
+        if world > 1:
+            allsums = [torch.zeros_like(sums) for _ in range(world)]
+            dist.all_gather(allsums, sums)
+            same = all(bool((a == allsums[0]).all()) for a in allsums)
+        else:
+            same = True
+        kname = KERNEL_NAMES[int(net.get_option("resolved_kernel"))]
+        entry = {"kernel": kname, "nvls_active": bool(net.get_option("nvls_active")), "all_ranks_identical": same}
+        if rank == 0:
+            from oracle import oracle as O
+            if expected is None:
+                sim = O.Simulation(world, desc.counts, desc.lr_mult, desc.decay_mult, seed=seed,
+                                   bf16=(desc.grad_dtype == "bf16"), **desc.hyper())
+                sim.step()
+                sim.step()
+                expected = (sim.consistent_weights(), sim.consistent_history())
+                del sim
+            gw = w.cpu().numpy()
+            gh = net.history()[o:o + n].cpu().numpy()
+            ew, eh = expected[0], expected[1][o:o + n]
+            bit = bool(np.array_equal(gw.view(np.uint32), ew.view(np.uint32)) and
+                       np.array_equal(gh.view(np.uint32), eh.view(np.uint32)))
+            den = np.maximum(np.abs(ew), 1e-30)
+            entry.update({"bit_exact": bit, "max_rel_err_weights": float(np.max(np.abs(gw - ew) / den)),
+                          "max_abs_err_history": float(np.max(np.abs(gh - eh))) if n else 0.0,
+                          "within_1e-5": bool(np.allclose(gw, ew, rtol=1e-5, atol=1e-8) and
+                                              np.allclose(gh, eh, rtol=1e-5, atol=1e-9))})
+        res[kname] = entry
+        if not net.sync():
+            raise RuntimeError(net.last_error())
+        net.deallocate()
+        if world > 1:
+            dist.barrier()
+    return res
+
+
+def measure_workload(torch, dist, C, harness, nets, args, name, grad_dtype, rank, world, local, primary):
+    """One workload, one net: device-resident `value`, host-blob `e2e`, in-step kernel time + roofline."""
+    bf16 = grad_dtype == "bf16"
+    desc = nets.solver_desc(name, grad_dtype=grad_dtype)
     batch = nets.NETS[name]["batch"]
     cl = harness.Cluster(desc, rank=rank, world=world, device=local)
     net = cl.net
@@ -163,13 +276,14 @@ def run_ours(args):
         net.set_option("algo", args.algo)
     net.set_option("kernel", args.kernel)
     net.set_option("nvls", int(args.nvls))
-    net.set_option("timing", 1)
     net.set_option("barrier_timeout_ms", 60000)
     prod = harness.make_producer(name, net)
     cl.start()
     P = net.param_count()
     mode = int(net.get_option("resolved_algo"))
     zero = int(net.get_option("zero_diff"))
+    kern = int(net.get_option("resolved_kernel"))
+    nvls = bool(net.get_option("nvls_active")) and kern == 3
 
     # synthetic batch: uniform[0,1) images, random labels; different per rank
     g = torch.Generator().manual_seed(1 + rank)
@@ -206,7 +320,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                loss_static = prod.forward_backward(x_dev, y_dev)
+                prod.forward_backward(x_dev, y_dev)
             net.diff().zero_()
         except Exception as e:  # eager fallback for the producer only (not the product path)
             graph = None
@@ -215,18 +329,21 @@ def run_ours(args):
             net.diff().zero_()
     torch.cuda.synchronize()
 
-    def step():
+    def fb():
         if graph is not None:
             graph.replay()
         else:
             prod.forward_backward(x_dev, y_dev)
+
+    def step():
+        fb()
         if not net.sync_step(0, torch.cuda.current_stream().cuda_stream):
             raise RuntimeError(net.last_error())
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and primary:
         sampler.start()
-    t_end = time.perf_counter() + 0.4  # nvidia-smi needs a moment to emit its first rows: same load meanwhile
+    t_end = time.perf_counter() + (0.4 if primary else 0.0)  # nvidia-smi needs a moment to emit its first rows
     spin = torch.tensor([1], device="cuda")
     while True:                        # collective: every rank runs the same number of extra steps
         for _ in range(10):
@@ -243,19 +360,16 @@ def run_ours(args):
     if not net.synchronize():
         raise RuntimeError(net.last_error())
 
-    # the fused kernel alone: library-side CUDA events around the launch, on the launching stream
+    # The fused kernel IN the step: library-side CUDA events around the one launch, on the launching stream,
+    # with forward/backward queued right in front of it (so the ranks arrive as they do in training: skewed by
+    # their own forward/backward times, gradients partly still in L2).  L2 flushed before each forward/backward.
+    net.set_option("timing", 1)
     kms = []
-    for _ in range(max(3, min(args.steps, 30))):
+    for _ in range(max(5, min(args.steps, 30))):
         flush()
-        if graph is not None:
-            graph.replay()
-        else:
-            prod.forward_backward(x_dev, y_dev)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        net.sync_step(0, torch.cuda.current_stream().cuda_stream)
-        kms.append(net.last_kernel_ms())
+        step()
+        kms.append(net.last_kernel_ms())  # waits for the launch
+    net.set_option("timing", 0)
     k_ms = sorted(kms)[len(kms) // 2]
     if world > 1:
         t = torch.tensor([k_ms], device="cuda", dtype=torch.float64)
@@ -266,7 +380,7 @@ def run_ours(args):
     for _ in range(10):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        graph.replay() if graph is not None else prod.forward_backward(x_dev, y_dev)
+        fb()
         b.record()
         fb_evs.append((a, b))
     torch.cuda.synchronize()
@@ -274,9 +388,12 @@ def run_ours(args):
     net.diff().zero_()
     torch.cuda.synchronize()
 
-    # end to end through the reference-facing API: train(solver_index, host blobs)
-    for _ in range(args.warmup):
+    # end to end through the reference-facing API: train(solver_index, host blobs).  train() double-buffers the
+    # input staging (H2D of batch t+1 overlaps step t) and reads the loss back every step; the timed region ends
+    # with synchronize(), i.e. when the last step's weights and loss are complete.
+    for _ in range(args.warmup + 2):
         assert net.train(0, [x_host, y_host]), net.last_error()
+    assert net.synchronize(), net.last_error()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -285,6 +402,8 @@ def run_ours(args):
     for _ in range(args.steps):
         if not net.train(0, [x_host, y_host]):
             raise RuntimeError(net.last_error())
+    if not net.synchronize():
+        raise RuntimeError(net.last_error())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_launches = net.launch_count() - e2e_launch0
@@ -293,50 +412,59 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     last_loss = net.last_loss()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and primary) else None
 
     peaks, peak_kind = measured_peaks()
-    hbm_b, nvl_b = algorithmic_bytes(P, world, mode, zero, bf16)
+    hbm_b, nvl_b = algorithmic_bytes(P, world, mode, zero, bf16, nvls=nvls, push=(kern == 2))
     if world == 1:
         bound, alg, peak = "hbm", hbm_b, float(peaks["hbm_gbs"])
     else:
         bound, alg, peak = "nvlink", nvl_b, NVLINK_MEASURED_GBS
     achieved = alg / (k_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{name}_n{world}")
-    except Exception:
-        pass
-
+    traffic, traffic_src = None, None
+    if world == 1:
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(f"{name}_n{world}")
+            traffic_src = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/traffic.json)"
+        except Exception:
+            pass
+    else:
+        tr = measure_nvlink_traffic(torch, dist, net, world, launches=50 if P > (1 << 22) else 400)
+        if tr is not None:
+            traffic = max(tr["data_tx"], tr["data_rx"])
+            traffic_src = ("NVML NVLink payload counters of this GPU around back-to-back launches, per launch: "
+                           f"tx {tr['data_tx']:.0f} B, rx {tr['data_rx']:.0f} B (raw incl. protocol: tx "
+                           f"{tr['raw_tx']:.0f} B, rx {tr['raw_rx']:.0f} B)")
+    kernel_fn = {0: "fused_sync_sgd_kernel", 1: "fused_sync_sgd_tma_kernel", 2: "fused_sync_sgd_push_kernel",
+                 3: "fused_sync_sgd_nvls_kernel"}[kern]
     out = {
-        "metric": "images/sec", "value": world * batch * args.steps / (total_ms * 1e-3), "unit": "images/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if not bf16 else "f32 (bf16 gradient wire)", "data": "synthetic",
+        "value": world * batch * args.steps / (total_ms * 1e-3), "unit": "images/s",
+        "ms_per_step": total_ms / args.steps,
+        "dtype": "f32" if not bf16 else "f32 (bf16 gradient wire)",
         "config": {"workload": f"{name} (batch {batch}/device, P={P} fp32 params), synchronous SGD: "
-                               f"PyTorch forward/backward + fused sync kernel",
-                   "global_batch": world * batch, "parallelism": f"dp{world}",
-                   "algo": {0: "local", 1: "two_shot", 2: "one_shot"}[mode], "grad_dtype": args.grad_dtype,
-                   "kernel": KERNEL_NAMES[int(net.get_option("resolved_kernel"))],
-                   "nvls": bool(net.get_option("nvls_active")),
-                   "producer": "cuda_graph" if graph is not None else "eager",
-                   "l2": "flushed between steps (256 MiB write outside the timed events)" if need_flush
-                         else f"working set {working_set >> 20} MiB > 126 MiB L2"},
-        "clocks": clocks,
+                               f"forward/backward + gradient sync + SGD update",
+                   "global_batch": world * batch, "parallelism": f"dp{world}"},
+        "impl_config": {"algo": {0: "local", 1: "two_shot", 2: "one_shot"}[mode], "grad_dtype": grad_dtype,
+                        "kernel": KERNEL_NAMES[kern], "nvls": nvls,
+                        "producer": "PyTorch/cuDNN forward/backward, " + ("cuda_graph" if graph is not None else "eager"),
+                        "l2": "flushed between steps (256 MiB write outside the timed events)" if need_flush
+                              else f"working set {working_set >> 20} MiB > 126 MiB L2"},
         "e2e": {"value": world * batch * args.steps / e2e_s, "unit": "images/s",
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
-                "timing": "host wall clock around K train() calls (each returns after the loss D2H), max over ranks",
-                "last_loss": last_loss},
+                "timing": "host wall clock around K train() calls + the final synchronize(); train() stages the "
+                          "batch from pinned host memory on a copy stream (double buffered) and reads the loss "
+                          "back every step; max over ranks", "last_loss": last_loss},
         "gpu_launches": int(launches), "e2e_gpu_launches": int(e2e_launches),
         "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": {0: "fused_sync_sgd_kernel", 1: "fused_sync_sgd_tma_kernel",
-                                2: "fused_sync_sgd_push_kernel", 3: "fused_sync_sgd_nvls_kernel"}[
-                         int(net.get_option("resolved_kernel"))], "kernel_ms": k_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_fn, "kernel_ms": k_ms,
+                     "kernel_ms_how": "median of CUDA-event times around the launch inside full steps",
                      "algorithmic_bytes": alg, "peak_source": (peak_kind + " MEASURED_PEAKS.json hbm_gbs") if
                      world == 1 else "B200_PROFILING.md measured peer copy per direction"},
         "split_ms": {"forward_backward": fb_ms, "fused_sync_kernel": k_ms},
     }
+    if clocks is not None:
+        out["clocks"] = clocks
     if world > 1:
         out["bus_gbs"] = 4 * P * 2 * (world - 1) / world / (k_ms * 1e-3) / 1e9
         # the library route the fused kernel replaces: NCCL all-reduce of the fp32 gradient (the SGD update
@@ -355,11 +483,62 @@ def run_ours(args):
         t = torch.tensor([sorted(nc)[len(nc) // 2]], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out["nccl_allreduce_only_ms"] = float(t.item())
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del buf
+    if rank == 0 and world == 1 and primary and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(name, desc, batch, 1, fb_ms)
-    if rank == 0 and args.kernels:
-        out["kernel_rooflines"] = kernel_rooflines(C, nets, peaks, world, args.kernel)
     net.deallocate()
+    del prod, graph
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    if world > 1:
+        dist.barrier()
+    return out, desc
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import caffeonspark_b200 as C
+    from caffeonspark_b200 import harness, nets
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.backends.cudnn.benchmark = not os.environ.get("COS_BENCH_NO_AUTOTUNE")  # off under ncu launch lists
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+
+    main, desc = measure_workload(torch, dist, C, harness, nets, args, args.workload, args.grad_dtype, rank, world,
+                                  local, primary=True)
+    out = {"metric": "images/sec", "value": main["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "data": "synthetic"}
+    out.update({k: v for k, v in main.items() if k not in ("value", "unit", "ms_per_step")})
+    # the other BASELINE configs as extra keys, each with its own roofline (config 2: LeNet; config 3:
+    # CIFAR-10-quick with the bf16 gradient wire)
+    if args.extras:
+        out["workloads"] = {}
+        for wname, gd in (("lenet", "fp32"), ("cifar10_quick", "bf16")):
+            if (wname, gd) == (args.workload, args.grad_dtype):
+                continue
+            r, _ = measure_workload(torch, dist, C, harness, nets, args, wname, gd, rank, world, local, primary=False)
+            out["workloads"][wname + ("_bf16" if gd == "bf16" else "")] = r
+    if world > 1 and not args.no_parity:
+        # what ran in the timed region (AUTO) and, when that is the NVLS kernel, the bit-exact P2P kernel too
+        kernels = [args.kernel]
+        if main["impl_config"]["kernel"] == KERNEL_NAMES[3]:
+            kernels.append(1)
+        par = parity_check(torch, dist, C, harness, desc, args.workload, rank, world, local, args, kernels)
+        out["parity"] = {"checked": True, "steps": 2, "against": "oracle.Simulation (C restatement pinned to the "
+                         "reference's socket_sync_cpu.cpp) on rank 0's host", "kernels": par,
+                         "bit_exact": all(v.get("bit_exact", False) for v in par.values() if not v["nvls_active"]) if
+                         rank == 0 else None,
+                         "all_within_1e-5": all(v.get("within_1e-5", False) for v in par.values()) if rank == 0 else None}
+    if rank == 0 and args.kernels:
+        out["kernel_rooflines"] = kernel_rooflines(C, nets, measured_peaks()[0], world, args.kernel)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -489,12 +668,49 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{name} (batch {batch}/device, P={desc.param_count} fp32 params), synchronous SGD: "
-                                  f"PyTorch forward/backward + reference CPU socket sync",
+                                  f"forward/backward + gradient sync + SGD update",
                       "global_batch": world * batch, "parallelism": f"dp{world}"},
+           "impl_config": {"sync": "the reference's own socket_sync_cpu.cpp + parallel_cpu.cpp + socket.cpp (oracle/_ref, "
+                                   f"{world} loopback processes on the host cores) + restated SGD update",
+                           "producer": "the same PyTorch/cuDNN forward/backward as the GPU arm (CUDA-graph replay)",
+                           "composition": "COMPOSED, not a joint loop: ms_per_step = median ms of the reference's "
+                                          "sync+update loop (measured inside ref_sync, first iteration dropped) + "
+                                          "median ms of forward/backward on the GPU; the two run back to back in "
+                                          "the reference as well (solver.cpp:221-240), so they add"},
            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample")},
+           "split_ms": {"forward_backward": fb_ms, "reference_cpu_sync_and_update": cb["sync_ms_per_iter"]},
            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
+
+
+def run_reference_sweep(args):
+    """Config 5, reference column: the reference's socket path (oracle/_ref) over the message sizes of the sweep
+    at N = --gpus loopback ranks on THIS box's host cores (bounded: few iterations per point)."""
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    if rank != 0:
+        return
+    world = max(world, args.gpus, 2)
+    from oracle import oracle as O
+    if not O.ref_available():
+        emit({"impl": "reference", "sweep": [], "unavailable": "oracle/_ref/ref_sync was not built"})
+        return
+    if args.sizes:
+        sizes = [int(float(x) * (1 << 20)) // 4 * 4 for x in args.sizes.split(",")]
+    else:
+        sizes = [64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20]
+    rows = []
+    for S in sizes:
+        P = S // 4
+        iters = max(3, min(40, int(4000 / max(1.0, S / 1e6 * world))))
+        r = O.run_ref_time(world, [P], iters=iters, lr_policy="fixed", base_lr=0.01, momentum=0.9, weight_decay=0.0005)
+        rows.append({"bytes": S, "ranks": world, "iters": iters, "ms_per_iter": r["ms_per_iter_median"],
+                     "ms_sync": r.get("ms_sync_median"), "cores": r.get("cores"),
+                     "bus_gbs": S * 2 * (world - 1) / world / (r["ms_per_iter_median"] * 1e-3) / 1e9})
+        print("[ref sweep] %8d KiB N=%d  %.3f ms/iter  bus %.3f GB/s" % (S >> 10, world, r["ms_per_iter_median"],
+                                                                         rows[-1]["bus_gbs"]), file=sys.stderr)
+    emit({"impl": "reference", "sweep": rows, "n_gpus": world, "host_cores": os.cpu_count(),
+          "what": "reference socket_sync_cpu path (on_start + on_gradients_ready + restated update), loopback TCP"})
 
 
 SWEEP_VARIANTS = {
@@ -621,10 +837,15 @@ def run_sweep(args):
                         dist.barrier()
                     net.sync_step(0)
                     net.synchronize()
-                    t = [net.get_option(f"trace_{i}") for i in range(5)]
-                    tr.append([(t[i + 1] - t[i]) / 1e3 for i in range(4)])
+                    t = [net.get_option(f"trace_{i}") for i in range(13)]
+                    # phases, then inside barrier A and B: release fence, flag flight + peer lateness, acquire fence
+                    tr.append([(t[i + 1] - t[i]) / 1e3 for i in range(4)] +
+                              [(t[6] - t[5]) / 1e3, (t[7] - t[6]) / 1e3, (t[8] - t[7]) / 1e3,
+                               (t[10] - t[9]) / 1e3, (t[11] - t[10]) / 1e3, (t[12] - t[11]) / 1e3])
                 net.set_option("trace", 0)
-                row["trace_us"] = [sorted(c)[len(c) // 2] for c in zip(*tr)]
+                med = [round(sorted(c)[len(c) // 2], 2) for c in zip(*tr)]
+                row["trace_us"] = med[:4]
+                row["barrier_us_fence_wait_acquire"] = {"A": med[4:7], "B": med[7:10]}
             if world > 1:
                 row["bus_gbs"] = S * 2 * (world - 1) / world / (k * 1e-3) / 1e9
             if world > 1 and nccl_ms is None:
@@ -654,7 +875,8 @@ def run_sweep(args):
             if rank == 0:
                 print("[sweep] %8d KiB %-7s %-18s nvls=%d  %.1f us (min %.1f, piped %.1f)  nccl %s  trace %s" % (
                     S >> 10, vname, row["kernel"], row["nvls_active"], k * 1e3, min(ms) * 1e3, piped * 1e3,
-                    "%.1f us" % (nccl_ms * 1e3) if nccl_ms else "-", row.get("trace_us")), file=sys.stderr)
+                    "%.1f us" % (nccl_ms * 1e3) if nccl_ms else "-",
+                    (row.get("trace_us"), row.get("barrier_us_fence_wait_acquire"))), file=sys.stderr)
             net.deallocate()
             if world > 1:
                 dist.barrier()
@@ -667,10 +889,15 @@ def run_sweep(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lenet", choices=["lenet", "cifar10_quick", "caffenet"])
+    ap.add_argument("--workload", default="caffenet", choices=["lenet", "cifar10_quick", "caffenet"],
+                    help="default: CaffeNet batch 256/device (BASELINE config 4, the largest single-GPU config)")
+    ap.add_argument("--extras", action="store_true", default=True,
+                    help="also measure LeNet (config 2) and CIFAR-10-quick with the bf16 wire (config 3) as extra keys")
+    ap.add_argument("--no-extras", dest="extras", action="store_false")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the seeded parity steps vs the oracle")
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 two-shot, 2 one-shot")
     ap.add_argument("--kernel", type=int, default=-1, help="-1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline")
@@ -688,7 +915,9 @@ def main():
     ap.add_argument("--sweep-max-bytes", type=int, default=1 << 40)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
-    if args.impl == "reference":
+    if args.impl == "reference" and args.sweep:
+        run_reference_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.sweep:
         run_sweep(args)

@@ -85,6 +85,7 @@ SYMBOLS = [
     ("cos_net_get_option", _i64, [_vp, _cp]),
     ("cos_net_last_kernel_ms", _f, [_vp]),
     ("cos_net_launch_count", _i64, [_vp]),
+    ("cos_net_fill", _i, [_vp, _i, _i, _u64, _u64, _f]),
     ("cos_adapter_create", _vp, [_i, _i]),
     ("cos_adapter_destroy", None, [_vp]),
     ("cos_adapter_address", _cp, [_vp]),

@@ -346,6 +346,12 @@ class CaffeNet:
     def launch_count(self):
         return self._L.cos_net_launch_count(self._h)
 
+    def fill(self, which, seed, stream, amp, solver_index=0):
+        """Seeded synthetic fill of data_ / diff_ / history on the device (same generator as the oracle's)."""
+        k = {"data": 0, "diff": 1, "history": 2}.get(which, which)
+        if not self._L.cos_net_fill(self._h, solver_index, int(k), int(seed), int(stream), float(amp)):
+            raise CosError(_err())
+
 
 class PeerAdapter:
     """cos_adapter: the SocketAdapter/SocketChannel analogue (control plane only)."""

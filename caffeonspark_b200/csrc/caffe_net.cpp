@@ -419,6 +419,18 @@ bool CaffeNet::synchronize(std::string* err) {
   return check_status(err);
 }
 
+bool CaffeNet::fill(int which, uint64_t seed, uint64_t stream_id, float amp, std::string* err) {
+  float* dst = which == 0 ? data_ : which == 1 ? diff_ : which == 2 ? hist_ : nullptr;
+  if (!dst) {
+    *err = "fill: which must be 0 (data), 1 (diff) or 2 (history)";
+    return false;
+  }
+  COS_RT(cudaSetDevice(device_));
+  COS_RT(launch_fill(dst, count_, seed, stream_id, amp, stream_));
+  COS_RT(cudaStreamSynchronize(stream_));
+  return true;
+}
+
 float CaffeNet::last_kernel_ms() {
   if (!ev_valid_) return -1.f;
   cudaSetDevice(device_);
@@ -575,8 +587,10 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "initial_gather") return opt_initial_gather_;
   if (name == "small_grid") return opt_small_grid_;
   if (name == "train_pipeline") return opt_train_pipeline_;
-  if (name.compare(0, 6, "trace_") == 0 && name.size() == 7 && name[6] >= '0' && name[6] <= '4')
-    return static_cast<int64_t>((reinterpret_cast<volatile unsigned long long*>(status_) + 2)[name[6] - '0']);
+  if (name.compare(0, 6, "trace_") == 0 && name.size() >= 7 && name.size() <= 8) {  // trace_0 .. trace_12
+    const int k = atoi(name.c_str() + 6);
+    if (k >= 0 && k <= 12) return static_cast<int64_t>((reinterpret_cast<volatile unsigned long long*>(status_) + 2)[k]);
+  }
   if (name == "transport") return arena_.transport();
   if (name == "default_grid") return default_sync_grid(device_);
   return -1;

@@ -61,6 +61,8 @@ class CaffeNet {
   bool sync_step(int solver_index, cudaStream_t stream, bool use_own_stream, std::string* err);
   bool all_gather_weights(cudaStream_t stream, bool use_own_stream, std::string* err);
   virtual bool synchronize(std::string* err);
+  // seeded device-side fill of data_ (0) / diff_ (1) / history (2), see cos_net_fill
+  bool fill(int which, uint64_t seed, uint64_t stream_id, float amp, std::string* err);
 
   virtual void set_forward_backward(cos_forward_backward_fn fn, void* user) { fb_fn_ = fn; fb_user_ = user; }
   void set_solver_index(int i) { solver_index_ = i; }

@@ -344,6 +344,17 @@ int64_t cos_net_get_option(cos_net* net, const char* name) {
 float cos_net_last_kernel_ms(cos_net* net) { return net ? R(net, 0)->last_kernel_ms() : -1.f; }
 int64_t cos_net_launch_count(cos_net* net) { return net ? N(net)->launch_count() : 0; }
 
+int cos_net_fill(cos_net* net, int solver_index, int which, uint64_t seed, uint64_t stream, float amp) {
+  COS_GUARD(0, {
+    if (!net) return fail("net is NULL");
+    CaffeNet* r = solver_index < 0 ? nullptr : R(net, solver_index);
+    if (!r) return fail("invalid solver_index");
+    std::string err;
+    if (!r->fill(which, seed, stream, amp, &err)) return fail(err);
+    return 1;
+  })
+}
+
 // ------------------------------------------------------------- adapter API
 
 cos_adapter* cos_adapter_create(int cluster_size, int rank) {

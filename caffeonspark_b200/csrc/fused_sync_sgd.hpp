@@ -55,7 +55,8 @@ struct SyncParams {
   uint32_t epoch;                   // barrier epoch of this launch
   unsigned long long timeout_ns;    // barrier time-out
   int* status;                      // local device word: 0 ok, else error code
-  unsigned long long* trace;        // optional: 5 x %globaltimer of CTA 0 (start, after A, after phase 1, after B, end)
+  unsigned long long* trace;        // optional: 13 x %globaltimer of CTA 0: [0..4] phase boundaries, [5..8] / [9..12]
+                                    // inside barrier A / B (entered, release fence done, flag arrived, acquire done)
 };
 
 // Launches the vector (LDG/STG) kernel.  grid/block 0 = defaults.

@@ -8,10 +8,12 @@
 // be zeroed after barrier B because peers read it.  Here every transfer is a
 // fire-and-forget STORE and nobody ever reads remote memory:
 //   phase 1  rank r stores shard q of its gradient into rank q's receive slot
-//            [r] (fp32 -> bf16 cast in registers: no wire buffer, no extra pass)
-//            and zeroes what it just read (ClearParamDiffs: nobody else reads
-//            diff_ in this scheme, so no barrier is needed for it);
-//   barrier A  "my contributions have landed in your slots";
+//            [r] (fp32 -> bf16 cast in registers: no wire buffer, no extra pass);
+//   barrier A  "my contributions have landed in your slots"; BETWEEN signalling
+//            and waiting, the CTA zeroes what it has just pushed (ClearParamDiffs:
+//            nobody else reads diff_ in this scheme, so it needs no barrier and
+//            hides in the flag flight; pure streaming stores -- a store right
+//            behind the load of the same line measured 3x slower on B200);
 //   phase 2  the owner reduces its own gradient + the N-1 slots out of LOCAL
 //            memory in the reference's order s, s+1, ... (mod N) with the 1/N
 //            scale applied before the sum (parallel_cpu.cpp:120-122,
@@ -19,7 +21,8 @@
 //            ComputeUpdateValue / Blob::Update (sgd_solver.cpp:145-243,
 //            blob.cpp:162-179) and stores the new weights locally and into every
 //            peer's data_ (the next on_start(), socket_sync_cpu.cpp:102-105);
-//   barrier B  "my weight stores have landed".
+//   barrier B  "my weight stores have landed" (own-shard diff_ zeroed between
+//            signal and wait).
 // The receive slots are the device-resident analogue of the reference's
 // diff_recv_ scratch buffers (socket_sync_cpu.cpp:14-44, one per peer, own_size_
 // elements).  They are safe to reuse every step without double buffering: a
@@ -91,48 +94,60 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // ---- phase 1: scatter my gradient into the owners' receive slots ----------
+  constexpr int kU = 4;  // loads in flight per thread
   for (int d = 1; d < world; ++d) {  // staggered destinations: at any moment the ranks target different peers
     int q = rank + d;
     if (q >= world) q -= world;
     const ShardRange r = shard_range(p.count, world, q);
     const uint64_t base = r.lo & ~3ull;  // slot element 0 <-> global element base (keeps float4 alignment)
-    if (BF16) {
-      uint16_t* dst = static_cast<uint16_t*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot;
-      for (uint64_t j = tid; j < r.nvec; j += stride) {
-        const uint64_t i = (r.vec_lo + j) << 2;
-        const float4 v = ld_stream(g + i);
-        if (zero) st_vec(g + i, z4);  // asm store: stays after the asm load above
-        const uint2 o = pack_bf16x4(v);
-        asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(dst + (i - base)), "r"(o.x), "r"(o.y) : "memory");
+    uint16_t* dst16 = static_cast<uint16_t*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot;
+    float* dst32 = static_cast<float*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot;
+    for (uint64_t j0 = tid; j0 < r.nvec; j0 += stride * kU) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
+        if (j < r.nvec) v[u] = ld_stream(g + ((r.vec_lo + j) << 2));
       }
-      if (blockIdx.x == 0) {
-        const uint64_t i = edge_element(r, threadIdx.x);
-        if (i != ~0ull) {
-          dst[i - base] = float_to_bf16_bits(g[i]);
-          if (zero) g[i] = 0.f;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
+        if (j < r.nvec) {
+          const uint64_t i = (r.vec_lo + j) << 2;
+          if (BF16) {
+            const uint2 o = pack_bf16x4(v[u]);
+            asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(dst16 + (i - base)), "r"(o.x), "r"(o.y) : "memory");
+          } else {
+            st_vec(dst32 + (i - base), v[u]);
+          }
         }
       }
-    } else {
-      float* dst = static_cast<float*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot;
-      for (uint64_t j = tid; j < r.nvec; j += stride) {
-        const uint64_t i = (r.vec_lo + j) << 2;
-        const float4 v = ld_stream(g + i);
-        if (zero) st_vec(g + i, z4);  // asm store: stays after the asm load above
-        st_vec(dst + (i - base), v);
-      }
-      if (blockIdx.x == 0) {
-        const uint64_t i = edge_element(r, threadIdx.x);
-        if (i != ~0ull) {
-          dst[i - base] = g[i];
-          if (zero) g[i] = 0.f;
-        }
+    }
+    if (blockIdx.x == 0) {
+      const uint64_t i = edge_element(r, threadIdx.x);
+      if (i != ~0ull) {
+        if (BF16) dst16[i - base] = float_to_bf16_bits(g[i]);
+        else dst32[i - base] = g[i];
       }
     }
   }
   if (tracer) p.trace[1] = globaltimer_ns();
 
   // ---- barrier A: every contribution to my shard has landed -----------------
-  if (!cta_barrier(p, 0, &s_abort)) return;
+  cta_signal(p, 0);
+  if (zero) {  // ClearParamDiffs of what this CTA pushed, hidden in the flag flight
+    for (int d = 1; d < world; ++d) {
+      int q = rank + d;
+      if (q >= world) q -= world;
+      const ShardRange r = shard_range(p.count, world, q);
+      for (uint64_t j = tid; j < r.nvec; j += stride) st_vec(g + ((r.vec_lo + j) << 2), z4);
+      if (blockIdx.x == 0) {
+        const uint64_t i = edge_element(r, threadIdx.x);
+        if (i != ~0ull) g[i] = 0.f;
+      }
+    }
+  }
+  if (!cta_wait(p, 0, &s_abort)) return;
   if (tracer) p.trace[2] = globaltimer_ns();
 
   // ---- phase 2: reduce (local), update, push the new weights ----------------
@@ -167,7 +182,6 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
       }
       float4 w = *reinterpret_cast<const float4*>(wl + i);
       float4 h = *reinterpret_cast<const float4*>(hl + i);
-      if (zero) st_vec(g + i, z4);  // asm store: stays after the asm load above
       if (BF16) {
         x[0].x = round_bf16(x[0].x); x[0].y = round_bf16(x[0].y);
         x[0].z = round_bf16(x[0].z); x[0].w = round_bf16(x[0].w);
@@ -221,7 +235,6 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
         SegCursor c2 = cur;
         c2.seek(i);
         float x = g[i];
-        if (zero) g[i] = 0.f;
         if (BF16) x = round_bf16(x);
         float acc = __fmul_rn(inv, x);
         for (int k = 1; k < world; ++k) {
@@ -247,7 +260,16 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
   if (tracer) p.trace[3] = globaltimer_ns();
 
   // ---- barrier B: every peer's weight shard has landed in my data_ ----------
-  if (!cta_barrier(p, 1, &s_abort)) return;
+  cta_signal(p, 1);
+  if (zero) {  // own shard of diff_: read by this CTA in phase 2 only
+    const ShardRange r = shard_range(p.count, world, rank);
+    for (uint64_t j = tid; j < r.nvec; j += stride) st_vec(g + ((r.vec_lo + j) << 2), z4);
+    if (blockIdx.x == 0) {
+      const uint64_t i = edge_element(r, threadIdx.x);
+      if (i != ~0ull) g[i] = 0.f;
+    }
+  }
+  if (!cta_wait(p, 1, &s_abort)) return;
   if (tracer) p.trace[4] = globaltimer_ns();
 }
 

@@ -97,15 +97,30 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   return v;
 }
 
+// Optional diagnostics (option "trace"): the first participating thread of CTA 0 stamps %globaltimer into
+// trace[5 + 4*which ...]: barrier entered (after __syncthreads), release fence done, flag arrived, acquire done.
+__device__ __forceinline__ bool barrier_tracer(const SyncParams& p) {
+  return p.trace != nullptr && blockIdx.x == 0 && static_cast<int>(threadIdx.x) == (p.rank == 0 ? 1 : 0);
+}
+
 __device__ __forceinline__ void cta_signal(const SyncParams& p, int which) {
   __syncthreads();
   const int t = threadIdx.x;
-  if (t < p.world && t != p.rank) st_release_sys(flag_slot(p.flags[t], which, blockIdx.x, p.rank), p.epoch);
+  if (t < p.world && t != p.rank) {
+    const bool tr = barrier_tracer(p);
+    if (tr) p.trace[5 + 4 * which] = globaltimer_ns();
+    asm volatile("fence.acq_rel.sys;" ::: "memory");  // release: cumulative over the bar.sync above
+    if (tr) p.trace[6 + 4 * which] = globaltimer_ns();
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag_slot(p.flags[t], which, blockIdx.x, p.rank)),
+                 "r"(p.epoch)
+                 : "memory");
+  }
 }
 
 __device__ __forceinline__ bool cta_wait(const SyncParams& p, int which, int* s_abort) {
   const int t = threadIdx.x;
   if (t < p.world && t != p.rank) {
+    const bool tr = barrier_tracer(p);
     const uint32_t* mine = flag_slot(p.flags[p.rank], which, blockIdx.x, t);
     const unsigned long long t0 = globaltimer_ns();
     unsigned spins = 0;
@@ -121,7 +136,9 @@ __device__ __forceinline__ bool cta_wait(const SyncParams& p, int which, int* s_
         }
       }
     }
+    if (tr) p.trace[7 + 4 * which] = globaltimer_ns();
     asm volatile("fence.acq_rel.sys;" ::: "memory");  // acquire: later loads see what the peer released
+    if (tr) p.trace[8 + 4 * which] = globaltimer_ns();
   }
   __syncthreads();
   return *reinterpret_cast<volatile int*>(s_abort) == 0;

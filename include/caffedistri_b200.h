@@ -211,15 +211,22 @@ COS_API int cos_net_synchronize(cos_net* net);
 
 /* Options: "algo" (COS_ALGO_*), "zero_diff" (0/1, default 1),
  * "grid" (CTAs, 0 = auto), "block" (threads, 0 = auto), "kernel" (-1 = auto,
- * 0 = LDG/STG vector kernel, 1 = TMA bulk-copy pipeline), "barrier_timeout_ms",
- * "one_shot_max_bytes", "timing" (CUDA events around each launch),
- * "initial_gather" (0 = connect() skips the first on_start(); the caller then
- * runs cos_net_all_gather_weights itself), "nvls" (1 = reduce / broadcast
- * through NVSwitch multicast when every rank can join; fp32 two-shot only;
- * matches the reference to 1e-5, not bitwise), "trace" (record %globaltimer at
- * the kernel's phase boundaries), "small_grid" (experimental grid sizing).
+ * 0 = LDG/STG pull kernel, 1 = TMA bulk-copy pull pipeline, 2 = push kernel
+ * (stores only, bf16 cast in registers), 3 = NVLS multimem kernel),
+ * "barrier_timeout_ms", "one_shot_max_bytes", "push_max_bytes" / "nvls_min_bytes"
+ * (AUTO thresholds on the message size 4P), "push_vecs" (push kernel grid sizing),
+ * "timing" (CUDA events around each launch, default 0), "initial_gather" (0 =
+ * connect() skips the first on_start(); the caller then runs
+ * cos_net_all_gather_weights itself), "nvls" (-1 = auto: join an NVSwitch
+ * multicast team at connect() when cluster_size >= 4, the wire is fp32 and
+ * 4P >= nvls_min_bytes; 0 = never; 1 = always try.  The in-switch sum matches the
+ * reference to 1e-5, not bitwise: set 0 for bit-exact runs), "nvls_unroll",
+ * "nvls_p2p" (share of plain-P2P vectors in the NVLS kernel), "train_pipeline"
+ * (1 = cos_net_train returns once its batch has left host memory; 0 = after the
+ * whole step), "trace" (record %globaltimer at the kernel's phase boundaries),
+ * "small_grid" (experimental grid sizing).
  * Read-only via get_option: "resolved_algo", "resolved_kernel", "nvls_active",
- * "transport", "default_grid", "trace_0".."trace_4".  1/0. */
+ * "transport", "default_grid", "trace_0".."trace_12".  1/0. */
 COS_API int cos_net_set_option(cos_net* net, const char* name, int64_t value);
 COS_API int64_t cos_net_get_option(cos_net* net, const char* name);
 
@@ -228,6 +235,12 @@ COS_API int64_t cos_net_get_option(cos_net* net, const char* name);
 COS_API float cos_net_last_kernel_ms(cos_net* net);
 /* Kernels launched by this net so far (bench.py gpu_launches). */
 COS_API int64_t cos_net_launch_count(cos_net* net);
+/* Seeded synthetic fill of one flat buffer ON THE DEVICE (which: 0 = data_, 1 = diff_,
+ * 2 = history): out[i] = amp * u_i, u_i uniform in [-1, 1) from a counter-based
+ * generator keyed by (seed, stream) -- the generator the oracle's driver uses
+ * (oracle/ref_driver.cpp), so benchmarks and parity runs need no host copy of the
+ * 4P-byte tensors.  Asynchronous on the net's stream; 1/0. */
+COS_API int cos_net_fill(cos_net* net, int solver_index, int which, uint64_t seed, uint64_t stream, float amp);
 
 /* --------------------- transport object (reference: util/socket.hpp) ------ */
 /* PeerAdapter = SocketAdapter + SocketChannel of the reference

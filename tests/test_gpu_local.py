@@ -226,3 +226,20 @@ def test_hdf5_snapshot_format_trains_but_refuses_to_snapshot(cos, tmp_path):
         assert not list(tmp_path.glob("c10_iter_*"))
     finally:
         net.deallocate()
+
+
+def test_device_fill_is_the_oracles_generator(cos, oracle):
+    """cos_net_fill (used by bench.py's N > 1 parity steps so that no 4P-byte tensor crosses PCIe) must produce
+    exactly the oracle driver's seeded tensors."""
+    desc = cos.SolverDesc([100003, 5], **HP_CIFAR)
+    net = cos.CaffeNet(desc)
+    try:
+        assert net.connect(net.localAddresses())
+        for which, view, seed, stream, amp in (("data", net.data, 42, 0, 0.05), ("diff", net.diff, 1234, 3 * 4096 + 7, 0.01),
+                                               ("history", net.history, 2**40 + 1, 2**33, 1.0)):
+            net.fill(which, seed, stream, amp)
+            assert_bits_equal(view().cpu().numpy(), oracle.fill(100008, seed, stream, amp), f"device fill of {which}")
+        with pytest.raises(cos.CosError):
+            net.fill(7, 1, 1, 1.0)
+    finally:
+        net.deallocate()

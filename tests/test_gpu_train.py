@@ -75,9 +75,11 @@ def test_train_two_ranks_in_process(cos, oracle):
 
         def run(r):
             out = []
-            for _ in range(6):
+            for t in range(6):
                 assert netz[r].train(0, list(batches[r])), netz[r].last_error()
-                out.append(netz[r].last_loss())  # pipelined: the newest loss that has ARRIVED (may lag a step)
+                if t == 0:  # pipelined train(): the loss arrives later; wait for the first one explicitly
+                    assert netz[r].synchronize(), netz[r].last_error()
+                out.append(netz[r].last_loss())  # otherwise: the newest loss that has ARRIVED (may lag a step)
             assert netz[r].synchronize(), netz[r].last_error()
             out.append(netz[r].last_loss())
             return out

@@ -337,7 +337,7 @@ def test_bench_algorithmic_byte_model_matches_design():
     # importing bench.py redirects fd 1; only load the function's source instead
     src = open(os.path.join(ROOT, "bench.py")).read()
     start = src.index("def algorithmic_bytes")
-    end = src.index("\ndef ", start + 10)
+    end = min(src.index("\ndef ", start + 10), src.index("\nclass ", start + 10))
     ns = {}
     exec(src[start:end], ns)
     f = ns["algorithmic_bytes"]
@@ -348,6 +348,9 @@ def test_bench_algorithmic_byte_model_matches_design():
     assert nvl == pytest.approx(8 * P * 7 / 8)                   # (b_g + 4) * P * (N-1)/N, b_g = 4
     assert f(P, 8, 1, 1, True)[1] == pytest.approx(6 * P * 7 / 8)  # bf16 wire
     assert f(P, 4, 2, 1, False)[1] == 4 * P * 3                   # one-shot pulls (N-1) full gradients
+    assert f(P, 8, 1, 1, False, nvls=True)[1] == pytest.approx(4 * P * 9 / 8)   # NVLS: 4P(1 + 1/N)
+    assert f(P, 8, 1, 1, True, push=True)[1] == pytest.approx(6 * P * 7 / 8)    # push: same wire bytes as pull
+    assert f(P, 8, 1, 1, True, push=True)[0] < f(P, 8, 1, 1, True)[0]           # ... without the cast pre-pass
     assert spec is not None
 
 
