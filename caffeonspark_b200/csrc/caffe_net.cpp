@@ -167,6 +167,13 @@ bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::str
     recv_stride_ = push_recv_stride(count_, world_);
     off = align_up(off + static_cast<size_t>(world_) * recv_stride_ * (spec_.grad_dtype == COS_GRAD_BF16 ? 2 : 4), 4096);
   }
+  if (world_ >= 2 && world_ <= 8 && fbytes <= kLLRegionMaxBytes) {  // LL kernel slots (small nets)
+    ll_slot_words(count_, world_, spec_.grad_dtype == COS_GRAD_BF16, &ll_grad_stride_, &ll_weight_stride_);
+    off_llg_ = off;
+    off = align_up(off + static_cast<size_t>(world_) * ll_grad_stride_ * 8, 4096);
+    off_llw_ = off;
+    off = align_up(off + static_cast<size_t>(world_) * ll_weight_stride_ * 8, 4096);
+  }
   const char* tr = getenv("COS_PEER_TRANSPORT");
   const bool prefer_vmm = peer_mappable && !(tr && strcmp(tr, "ipc") == 0);
   if (!arena_.create(dev, off, prefer_vmm, err)) return false;
@@ -182,6 +189,8 @@ bool CaffeNet::allocate_device(int start_device_id, bool peer_mappable, std::str
   peer_flags_[rank_] = reinterpret_cast<uint32_t*>(base);
   recv_ = recv_stride_ ? static_cast<void*>(base + off_recv_) : nullptr;
   peer_recv_[rank_] = recv_;
+  peer_llg_[rank_] = ll_grad_stride_ ? reinterpret_cast<uint64_t*>(base + off_llg_) : nullptr;
+  peer_llw_[rank_] = ll_grad_stride_ ? reinterpret_cast<uint64_t*>(base + off_llw_) : nullptr;
 
   // blob (segment) table: cumulative ends + multipliers
   std::vector<uint64_t> ends;
@@ -254,9 +263,9 @@ int CaffeNet::resolved_algo() const {
 // dtype, options, NVLS team) -- all identical on every rank -- so every rank resolves the same variant, which
 // the per-CTA barriers require.  AUTO, from the B200 measurements under profiles/:
 //   * N >= 4, fp32 wire, multicast team up, 4P >= nvls_min_bytes: NVLS (half the NVLink bytes of P2P);
-//   * bf16 wire: push (the only variant whose cast costs no extra pass);
-//   * 4P < push_max_bytes: push (stores only, two store round trips on the critical path);
-//   * otherwise the TMA pull pipeline.
+//   * 4P < ll_max_bytes (N <= 8): LL -- flag-in-data words, no barrier, no fence (latency-bound sizes);
+//   * otherwise push (stores only; the bf16 cast costs no extra pass; measured >= the TMA pull pipeline at
+//     every size on B200), the TMA pull pipeline above push_max_bytes.
 // A forced variant that cannot run the current mode falls back to AUTO's choice.
 int CaffeNet::resolved_kernel() const {
   const int algo = resolved_algo();
@@ -264,12 +273,15 @@ int CaffeNet::resolved_kernel() const {
   const int64_t bytes = static_cast<int64_t>(count_ * sizeof(float));
   const bool nvls_ok = nvls_active_ && fp32 && algo == kModeTwoShot;
   const bool push_ok = world_ > 1 && algo == kModeTwoShot && recv_stride_ > 0;
+  const bool ll_ok = world_ > 1 && algo == kModeTwoShot && ll_grad_stride_ > 0;
   if (opt_kernel_ == 0 || opt_kernel_ == 1) return opt_kernel_;
   if (opt_kernel_ == 2 && push_ok) return 2;
   if (opt_kernel_ == 3 && nvls_ok) return 3;
+  if (opt_kernel_ == 4 && ll_ok) return 4;
   if (world_ == 1) return 0;
   if (algo != kModeTwoShot) return bytes >= (2 << 20) ? 1 : 0;
   if (nvls_ok && (opt_nvls_ == 1 || (world_ >= 4 && bytes >= opt_nvls_min_bytes_))) return 3;
+  if (ll_ok && bytes < opt_ll_max_bytes_) return 4;
   if (push_ok && (!fp32 || bytes < opt_push_max_bytes_)) return 2;
   return bytes >= (2 << 20) ? 1 : 0;
 }
@@ -299,8 +311,12 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
     p.wire[r] = peer_wire_[r];
     p.flags[r] = peer_flags_[r];
     p.recv[r] = peer_recv_[r];
+    p.ll_grad[r] = peer_llg_[r];
+    p.ll_weight[r] = peer_llw_[r];
   }
   p.recv_stride = recv_stride_;
+  p.ll_grad_stride = ll_grad_stride_;
+  p.ll_weight_stride = ll_weight_stride_;
   p.nvls_unroll = opt_nvls_unroll_;
   p.nvls_p2p = opt_nvls_p2p_;
   p.use_nvls = nvls_active_ ? 1 : 0;
@@ -346,6 +362,7 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
     case 1: e = launch_fused_sync_sgd_tma(p, grid, stream); break;
     case 2: e = launch_fused_sync_sgd_push(p, grid, opt_block_, opt_push_vecs_, stream); break;
     case 3: e = launch_fused_sync_sgd_nvls(p, grid, stream); break;
+    case 4: e = launch_fused_sync_sgd_ll(p, grid, opt_block_, opt_push_vecs_, stream); break;
     default: e = launch_fused_sync_sgd(p, grid, opt_block_, stream); break;
   }
   if (e != cudaSuccess) {
@@ -394,6 +411,12 @@ bool CaffeNet::check_status(std::string* err) {
   if (s == 0) return true;
   *reinterpret_cast<volatile int*>(status_) = 0;
   std::ostringstream os;
+  if (s >= 200 && s < 200 + kMaxRanks) {  // fused_sync_sgd_ll.cu: a peer's flagged words never arrived
+    os << "device-side LL exchange timed out after " << opt_timeout_ms_ << " ms waiting for data "
+       << (s - 200 == rank_ ? "of a peer" : "of rank " + std::to_string(s - 200)) << " (status " << s << ")";
+    *err = os.str();
+    return false;
+  }
   if (s == 300) {  // fused_sync_sgd_tma.cu: an mbarrier never completed (a bulk copy was lost or a peer died mid-tile)
     os << "device-side TMA pipeline timed out after " << opt_timeout_ms_
        << " ms waiting for a bulk copy to complete (status 300)";
@@ -551,6 +574,7 @@ bool CaffeNet::set_option(const std::string& name, int64_t v, std::string* err) 
   else if (name == "nvls_p2p") opt_nvls_p2p_ = static_cast<int>(v);
   else if (name == "push_vecs") opt_push_vecs_ = static_cast<int>(v);
   else if (name == "push_max_bytes") opt_push_max_bytes_ = v;
+  else if (name == "ll_max_bytes") opt_ll_max_bytes_ = v;
   else if (name == "nvls_min_bytes") opt_nvls_min_bytes_ = v;
   else if (name == "barrier_timeout_ms") opt_timeout_ms_ = v;
   else if (name == "one_shot_max_bytes") opt_one_shot_max_bytes_ = v;
@@ -581,6 +605,7 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "nvls_p2p") return opt_nvls_p2p_;
   if (name == "push_vecs") return opt_push_vecs_;
   if (name == "push_max_bytes") return opt_push_max_bytes_;
+  if (name == "ll_max_bytes") return opt_ll_max_bytes_;
   if (name == "nvls_min_bytes") return opt_nvls_min_bytes_;
   if (name == "barrier_timeout_ms") return opt_timeout_ms_;
   if (name == "one_shot_max_bytes") return opt_one_shot_max_bytes_;
@@ -870,6 +895,8 @@ bool NvlinkCaffeNet::connect(const std::vector<std::string>& addresses, std::str
     peer_hist_[peer] = reinterpret_cast<const float*>(base + off_hist_);
     peer_wire_[peer] = wire_ ? reinterpret_cast<uint16_t*>(base + off_wire_) : nullptr;
     peer_recv_[peer] = recv_stride_ ? static_cast<void*>(base + off_recv_) : nullptr;
+    peer_llg_[peer] = ll_grad_stride_ ? reinterpret_cast<uint64_t*>(base + off_llg_) : nullptr;
+    peer_llw_[peer] = ll_grad_stride_ ? reinterpret_cast<uint64_t*>(base + off_llw_) : nullptr;
   }
   connected_ = true;
   // NVLS multicast team: on request, or by default where it pays (N >= 4, message >= nvls_min_bytes, fp32 wire).

@@ -104,6 +104,8 @@ class CaffeNet {
   size_t off_data_ = 0, off_diff_ = 0, off_hist_ = 0, off_wire_ = 0, off_recv_ = 0;
   uint64_t recv_stride_ = 0;       // elements per receive slot of the push kernel (0: no receive region)
   void* recv_ = nullptr;           // [world][recv_stride_] fp32 or bf16: the reference's diff_recv_ scratch, on device
+  size_t off_llg_ = 0, off_llw_ = 0;  // LL kernel slots (small nets only): [world][ll_*_stride_] 8-byte words
+  uint64_t ll_grad_stride_ = 0, ll_weight_stride_ = 0;
   float* data_ = nullptr;
   float* diff_ = nullptr;
   uint16_t* wire_ = nullptr;
@@ -124,6 +126,8 @@ class CaffeNet {
   const float* peer_hist_[kMaxRanks] = {};
   uint32_t* peer_flags_[kMaxRanks] = {};
   void* peer_recv_[kMaxRanks] = {};
+  uint64_t* peer_llg_[kMaxRanks] = {};
+  uint64_t* peer_llw_[kMaxRanks] = {};
   bool connected_ = false;
   bool nvls_active_ = false;        // multicast object bound on every rank (NvlinkCaffeNet::setup_nvls)
   char* mc_base_ = nullptr;         // multicast VA of the arena
@@ -141,13 +145,14 @@ class CaffeNet {
   int opt_algo_ = COS_ALGO_AUTO;
   int opt_zero_diff_ = 1;
   int opt_grid_ = 0, opt_block_ = 0;
-  int opt_kernel_ = -1;  // -1 auto, 0 LDG/STG vector kernel, 1 TMA bulk-copy pipeline, 2 push, 3 NVLS (multimem)
+  int opt_kernel_ = -1;  // -1 auto, 0 LDG/STG pull, 1 TMA bulk-copy pull, 2 push, 3 NVLS (multimem), 4 LL (fence-free)
   int opt_timing_ = 0;   // CUDA events around every launch (cos_net_last_kernel_ms); benchmarks turn it on
   int opt_nvls_ = -1;    // -1 auto (multicast team when world >= 4 and 4P >= nvls_min_bytes), 0 off, 1 on
   int opt_nvls_unroll_ = 4;     // switch loads in flight per thread
   int opt_nvls_p2p_ = 0;        // 1: one plain-P2P vector per nvls_unroll switch vectors (link + switch both busy)
   int opt_push_vecs_ = 2;       // push kernel: float4 vectors per thread of the owner phase (sizes the grid)
-  int64_t opt_push_max_bytes_ = 8 << 20;   // AUTO: push kernel below this message size (4P bytes), fp32 wire
+  int64_t opt_push_max_bytes_ = int64_t(1) << 40;  // AUTO: push kernel below this message size (4P bytes), fp32 wire
+  int64_t opt_ll_max_bytes_ = 2 << 20;     // AUTO: LL kernel below this message size (and <= kLLRegionMaxBytes)
   int64_t opt_nvls_min_bytes_ = 2 << 20;   // AUTO: NVLS kernel at or above this message size when world >= 4
   int opt_small_grid_ = 0;      // experimental: size the grid by the reduce phase (see CaffeNet::launch)
   int opt_trace_ = 0;           // record %globaltimer at the phase boundaries of CTA 0 (diagnostics)

@@ -39,6 +39,10 @@ struct SyncParams {
   uint32_t* flags[kMaxRanks];       // flag region of every rank
   void* recv[kMaxRanks];            // push kernel: receive slots of every rank ([src][recv_stride] fp32 or bf16)
   uint64_t recv_stride;             // elements per receive slot
+  uint64_t* ll_grad[kMaxRanks];     // LL kernel: gradient slots of every rank ([src][ll_grad_stride] 8-byte words)
+  uint64_t* ll_weight[kMaxRanks];   // LL kernel: weight slots of every rank ([src][ll_weight_stride] words)
+  uint64_t ll_grad_stride;          // words per LL gradient slot (0: no LL region)
+  uint64_t ll_weight_stride;        // words per LL weight slot
   float* mc_data;                   // NVLS: multicast address of data_ (a store lands on every rank)
   const float* mc_diff;             // NVLS: multicast address of diff_ (a load returns the in-switch sum)
   int use_nvls;                     // two-shot only: multimem.ld_reduce / multimem.st instead of P2P
@@ -70,6 +74,13 @@ cudaError_t launch_fused_sync_sgd_push(const SyncParams& p, int grid, int block,
                                        cudaStream_t stream);
 // Launches the NVLS (multimem) variant with optional P2P share (fused_sync_sgd_nvls.cu).
 cudaError_t launch_fused_sync_sgd_nvls(const SyncParams& p, int grid, cudaStream_t stream);
+// Launches the low-latency (flag-in-data, fence-free) variant for small nets; world sizes 2..8.
+cudaError_t launch_fused_sync_sgd_ll(const SyncParams& p, int grid, int block, int vecs_per_thread,
+                                     cudaStream_t stream);
+// 8-byte words per LL gradient / weight slot for (count, world, wire dtype).
+void ll_slot_words(uint64_t count, int world, bool bf16, uint64_t* grad_words, uint64_t* weight_words);
+// Largest message (4P bytes) an LL region is allocated for.
+constexpr uint64_t kLLRegionMaxBytes = 8ull << 20;
 // Elements per receive slot of the push kernel for (count, world).
 uint64_t push_recv_stride(uint64_t count, int world);
 // Occupancy-derived default grid (co-resident CTAs) for the vector kernel.

@@ -69,11 +69,11 @@ MAX_INPROC = 4
 
 @pytest.mark.parametrize("name", sorted(k for k, m in _cases().items() if m["N"] <= MAX_INPROC))
 @pytest.mark.parametrize("algo", [1, 2])
-@pytest.mark.parametrize("kernel", [0, 1, 2], ids=["ldg", "tma", "push"])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 4], ids=["ldg", "tma", "push", "ll"])
 def test_matches_reference_golden_vectors(cos, oracle, name, algo, kernel):
     """Directly against vectors produced by the reference's own code."""
-    if kernel == 2 and algo == 2:
-        pytest.skip("the push kernel is two-shot only")
+    if kernel in (2, 4) and algo == 2:
+        pytest.skip("the push and LL kernels are two-shot only")
     m = _cases()[name]
     gold = np.load(os.path.join(GOLD, "ref_sync_cases.npz"))
     R, sim = _run_case(cos, oracle, m["N"], m["counts"], m["lr_mult"], m["decay_mult"], m["hyper"], m["iters"],
@@ -89,20 +89,20 @@ def test_matches_reference_golden_vectors(cos, oracle, name, algo, kernel):
 
 @pytest.mark.parametrize("N", [2, 3, 4])
 @pytest.mark.parametrize("algo", [1, 2])
-@pytest.mark.parametrize("kernel", [0, 1, 2], ids=["ldg", "tma", "push"])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 4], ids=["ldg", "tma", "push", "ll"])
 def test_lenet_layout_world_sizes(cos, oracle, N, algo, kernel):
-    if kernel == 2 and algo == 2:
-        pytest.skip("the push kernel is two-shot only")
+    if kernel in (2, 4) and algo == 2:
+        pytest.skip("the push and LL kernels are two-shot only")
     counts = [500, 20, 25000, 50, 40000, 500, 5000, 10]  # LeNet blob structure, ip1 shrunk to keep it quick
     R, _ = _run_case(cos, oracle, N, counts, [1, 2] * 4, [1, 1] * 4, HP, 3, 31, algo=algo, kernel=kernel)
     R.close()
 
 
 @pytest.mark.parametrize("N,algo", [(2, 1), (3, 1), (4, 1), (4, 2)])
-@pytest.mark.parametrize("kernel", [0, 1, 2], ids=["ldg", "tma", "push"])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 4], ids=["ldg", "tma", "push", "ll"])
 def test_bf16_wire(cos, oracle, N, algo, kernel):
-    if kernel == 2 and algo == 2:
-        pytest.skip("the push kernel is two-shot only")
+    if kernel in (2, 4) and algo == 2:
+        pytest.skip("the push and LL kernels are two-shot only")
     counts = [2400, 32, 25600, 32, 5120, 64, 6553, 64, 640, 10]
     hp = dict(lr_policy="fixed", base_lr=0.001, momentum=0.9, weight_decay=0.004)
     R, _ = _run_case(cos, oracle, N, counts, [1, 2] * 5, [1, 1] * 5, hp, 3, 41, bf16=True, algo=algo, kernel=kernel)
@@ -117,40 +117,46 @@ def test_first_on_start_reconciles_different_initial_weights(cos, oracle):
 def test_generic_world_size_and_odd_shapes(cos, oracle):
     # odd sizes, tiny P < N (empty shards), P == N, both kernels
     for N, counts in [(3, [997, 3]), (4, [64, 1]), (4, [3]), (4, [4]), (3, [1]), (2, [9, 8, 7])]:
-        for algo, kernel in ((1, 0), (1, 1), (1, 2), (2, 0), (2, 1)):
+        for algo, kernel in ((1, 0), (1, 1), (1, 2), (1, 4), (2, 0), (2, 1)):
             R, _ = _run_case(cos, oracle, N, counts, None, None, HP, 2, 61, algo=algo, kernel=kernel)
             assert R.nets[0].get_option("resolved_kernel") == kernel
             R.close()
     # bf16 wire through the push kernel on the same odd shapes (2-byte slots, 8-byte vectors)
     for N, counts in [(3, [997, 3]), (4, [3]), (2, [9, 8, 7])]:
-        R, _ = _run_case(cos, oracle, N, counts, None, None, HP, 2, 62, bf16=True, algo=1, kernel=2)
-        R.close()
+        for kernel in (2, 4):
+            R, _ = _run_case(cos, oracle, N, counts, None, None, HP, 2, 62, bf16=True, algo=1, kernel=kernel)
+            R.close()
 
 
 def test_push_kernel_many_vectors_per_thread_and_grid_sizes(cos, oracle):
     """The push kernel's grid is sized by the owner's shard (push_vecs float4 per thread); every sizing must
     give the same bits, including grids much smaller than the work (each thread loops)."""
     counts = [500, 20, 25000, 50, 40000, 500, 5000, 10]
-    for grid, block in ((1, 32), (3, 64), (7, 128)):
-        R, _ = _run_case(cos, oracle, 3, counts, [1, 2] * 4, [1, 1] * 4, HP, 2, 33, algo=1, kernel=2, grid=grid,
-                         block=block)
-        R.close()
+    for kernel in (2, 4):
+        for grid, block in ((1, 32), (3, 64), (7, 128)):
+            R, _ = _run_case(cos, oracle, 3, counts, [1, 2] * 4, [1, 1] * 4, HP, 2, 33, algo=1, kernel=kernel,
+                             grid=grid, block=block)
+            R.close()
 
 
 def test_auto_kernel_selection(cos):
-    """AUTO: push below push_max_bytes (fp32) and always for the bf16 wire, TMA pull above; forced variants that
-    cannot run fall back.  (NVLS needs a multicast team, i.e. real multi-GPU: test_gpu_multiproc.py.)"""
+    """AUTO: LL below ll_max_bytes, push above (and always for the bf16 wire), TMA pull above push_max_bytes;
+    forced variants that cannot run fall back.  (NVLS needs a multicast team, i.e. real multi-GPU:
+    test_gpu_multiproc.py.)"""
     small, big = cos.SolverDesc([100000], **HP), cos.SolverDesc([3 << 20], **HP)
     big16 = cos.SolverDesc([3 << 20], grad_dtype="bf16", **HP)
-    for desc, want in ((small, 2), (big, 1), (big16, 2)):
+    for desc, want in ((small, 4), (big, 2), (big16, 2)):
         net = cos.CaffeNet(desc, "", "", 1, 2, 0, True, cos.CaffeNet.SOCKET, -1, 0)
         try:
             assert net.get_option("resolved_kernel") == want
             net.set_option("kernel", 3)               # no multicast team: falls back to AUTO
             assert net.get_option("resolved_kernel") == want
+            net.set_option("kernel", 4)               # no LL region above 8 MiB: falls back to AUTO
+            assert net.get_option("resolved_kernel") == want
             net.set_option("kernel", 0)
             assert net.get_option("resolved_kernel") == 0
             net.set_option("kernel", -1)
+            net.set_option("ll_max_bytes", 0)
             net.set_option("push_max_bytes", 0)
             assert net.get_option("resolved_kernel") == (2 if desc is big16 else (1 if desc is big else 0))
         finally:

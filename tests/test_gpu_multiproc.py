@@ -88,7 +88,7 @@ def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0, nvls=F
 
 @pytest.mark.skipif(gpu_count() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("algo,bf16,kernel", [(1, False, 0), (2, False, 0), (1, True, 0), (1, False, 1), (2, False, 1),
-                                              (1, True, 1), (1, False, 2), (1, True, 2)])
+                                              (1, True, 1), (1, False, 2), (1, True, 2), (1, False, 4), (1, True, 4)])
 def test_one_process_per_gpu_bit_exact(cos, oracle, algo, bf16, kernel):
     import torch.multiprocessing as mp
     world = min(gpu_count(), 8)
@@ -138,7 +138,7 @@ def test_nvls_two_shot_within_tolerance(cos, oracle, unroll, p2p):
 @pytest.mark.skipif(gpu_count() < 1, reason="needs a GPU")
 @pytest.mark.parametrize("world,algo,bf16,kernel", [(2, 1, False, 0), (3, 2, False, 1), (5, 1, True, 0),
                                                     (8, 1, False, 1), (8, 2, False, 0), (5, 1, False, 2),
-                                                    (8, 1, True, 2)])
+                                                    (8, 1, True, 2), (3, 1, False, 4), (8, 1, True, 4)])
 def test_processes_sharing_one_gpu_bit_exact(cos, oracle, world, algo, bf16, kernel):
     """Several executor PROCESSES on the single test GPU: the cross-process
     descriptor-passing / VMM import path and the device-side barriers between
