@@ -44,7 +44,8 @@ class SolverDesc:
 
     def __init__(self, counts, lr_mult=None, decay_mult=None, lr_policy="fixed", base_lr=0.01, gamma=0.0, power=0.0,
                  stepsize=1, stepvalues=(), max_iter=0, momentum=0.0, weight_decay=0.0, test_iter=0,
-                 test_interval=0, snapshot_prefix="", grad_dtype="fp32", init_iter=0, batch_size=0):
+                 test_interval=0, snapshot_prefix="", grad_dtype="fp32", init_iter=0, batch_size=0,
+                 regularization_type="L2"):
         self.counts = [int(c) for c in counts]
         self.lr_mult = [float(x) for x in (lr_mult if lr_mult is not None else [1.0] * len(self.counts))]
         self.decay_mult = [float(x) for x in (decay_mult if decay_mult is not None else [1.0] * len(self.counts))]
@@ -53,6 +54,7 @@ class SolverDesc:
         self.momentum, self.weight_decay = momentum, weight_decay
         self.test_iter, self.test_interval, self.snapshot_prefix = test_iter, test_interval, snapshot_prefix
         self.grad_dtype, self.init_iter, self.batch_size = grad_dtype, init_iter, batch_size
+        self.regularization_type = regularization_type
 
     @property
     def param_count(self):
@@ -62,7 +64,8 @@ class SolverDesc:
         """Keyword arguments understood by oracle.Simulation / run_ref_*."""
         return dict(lr_policy=self.lr_policy, base_lr=self.base_lr, gamma=self.gamma, power=self.power,
                     stepsize=self.stepsize, stepvalues=self.stepvalues, max_iter=self.max_iter,
-                    momentum=self.momentum, weight_decay=self.weight_decay)
+                    momentum=self.momentum, weight_decay=self.weight_decay,
+                    regularization_type=self.regularization_type)
 
     def to_c(self):
         n = len(self.counts)
@@ -79,6 +82,7 @@ class SolverDesc:
         d.test_iter, d.test_interval, d.snapshot_prefix = int(self.test_iter), int(self.test_interval), keep["pre"]
         d.grad_dtype = 1 if self.grad_dtype == "bf16" else 0
         d.init_iter = int(self.init_iter)
+        d.regularization_l1 = 1 if self.regularization_type == "L1" else 0
         return d, keep
 
 
@@ -97,7 +101,8 @@ def parse_solver(solver_conf_file):
     return SolverDesc(list(c[:n]), list(lm[:n]), list(dm[:n]), lr_policy=pol.value.decode(), base_lr=d.base_lr,
                       gamma=d.gamma, power=d.power, stepsize=d.stepsize, stepvalues=list(sv[:d.nstepvalues]),
                       max_iter=d.max_iter, momentum=d.momentum, weight_decay=d.weight_decay, test_iter=d.test_iter,
-                      test_interval=d.test_interval, snapshot_prefix=pre.value.decode(), batch_size=bs.value)
+                      test_interval=d.test_interval, snapshot_prefix=pre.value.decode(), batch_size=bs.value,
+                      regularization_type="L1" if d.regularization_l1 else "L2")
 
 
 def read_caffemodel_blob(path, layer_name, blob_index=0):

@@ -303,6 +303,7 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
   p.mode = mode;
   p.grad_bf16 = spec_.grad_dtype == COS_GRAD_BF16;
   p.zero_diff = opt_zero_diff_;
+  p.l1 = spec_.regularization_type == "L1" ? 1 : 0;
   p.nseg = nseg_;
   p.count = count_;
   for (int r = 0; r < world_; ++r) {

@@ -77,6 +77,7 @@ bool spec_from_desc(const cos_solver_desc* d, SolverSpec* s, std::string* err) {
   s->snapshot_prefix = d->snapshot_prefix ? d->snapshot_prefix : "";
   s->grad_dtype = d->grad_dtype;
   s->init_iter = d->init_iter;
+  s->regularization_type = d->regularization_l1 ? "L1" : "L2";
   float r;
   int step = 0;
   if (!cosb::learning_rate(s->lr_policy, s->base_lr, s->gamma, s->power, s->stepsize,
@@ -559,6 +560,7 @@ int cos_parse_solver(const char* solver_conf_file, cos_solver_desc* desc, int64_
     desc->max_iter = s.max_iter;
     desc->momentum = s.momentum;
     desc->weight_decay = s.weight_decay;
+    desc->regularization_l1 = s.regularization_type == "L1" ? 1 : 0;
     desc->test_iter = s.test_iter;
     desc->test_interval = s.test_interval;
     if (batch_size) *batch_size = s.batch_size;

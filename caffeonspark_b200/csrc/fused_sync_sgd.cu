@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kDefaultThreads, 2) fused_sync_sgd_kernel(cons
           if (BF16 && p.mode == kModeLocal) g = bf16_bits_to_float(float_to_bf16_bits(g));
           float w = wl[i], h = hl[i];
           sgd_element(g, w, h, __fmul_rn(p.rate, c2.lr_mult[c2.k]), __fmul_rn(p.weight_decay, c2.decay_mult[c2.k]),
-                      p.momentum);
+                      p.momentum, p.l1);
           hl[i] = h;
           wl[i] = w;
           if (push) {

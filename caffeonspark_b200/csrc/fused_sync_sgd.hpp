@@ -31,6 +31,7 @@ struct SyncParams {
   int mode;
   int grad_bf16;   // reduce over the bf16 wire buffers (cast fused in phase 0)
   int zero_diff;   // fold the next Step's ClearParamDiffs into the kernel
+  int l1;          // regularization_type: 0 = L2 (g += ld*w), 1 = L1 (g += ld*sign(w))
   int nseg;
   uint64_t count;  // P: fp32 elements in data_/diff_/history
   float* data[kMaxRanks];           // data_ of every rank ([rank] is local)

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kLLThreads, 1) fused_sync_sgd_ll_kernel(const 
         if (alive) {
           float w = wl[e], h = hl[e];
           sgd_element(acc, w, h, __fmul_rn(p.rate, c2.lr_mult[c2.k]), __fmul_rn(p.weight_decay, c2.decay_mult[c2.k]),
-                      p.momentum);
+                      p.momentum, p.l1);
           hl[e] = h;
           wl[e] = w;
           for (int k = 1; k < world; ++k) {

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
       }
       float w = wl[i], h = hl[i];
       sgd_element(acc, w, h, __fmul_rn(p.rate, cur.lr_mult[cur.k]), __fmul_rn(p.weight_decay, cur.decay_mult[cur.k]),
-                  p.momentum);
+                  p.momentum, p.l1);
       hl[i] = h;
       wl[i] = w;
       for (int k = 1; k < world; ++k) {

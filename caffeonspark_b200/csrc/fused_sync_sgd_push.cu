@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
         }
         float w = wl[i], h = hl[i];
         sgd_element(acc, w, h, __fmul_rn(p.rate, c2.lr_mult[c2.k]), __fmul_rn(p.weight_decay, c2.decay_mult[c2.k]),
-                    p.momentum);
+                    p.momentum, p.l1);
         hl[i] = h;
         wl[i] = w;
         for (int k = 1; k < world; ++k) {

@@ -393,7 +393,7 @@ fused_sync_sgd_tma_kernel(const SyncParams p, const int tile_elems) {
         }
         float w = wl[i], h = hl[i];
         sgd_element(g, w, h, __fmul_rn(p.rate, c2.lr_mult[c2.k]), __fmul_rn(p.weight_decay, c2.decay_mult[c2.k]),
-                    p.momentum);
+                    p.momentum, p.l1);
         hl[i] = h;
         wl[i] = w;
         if (push) {

@@ -505,8 +505,8 @@ bool parse_solver_prototxt(const std::string& solver_path, SolverSpec* spec, std
     *err = "solver type '" + spec->type + "' is not on the accelerated path (only SGD with momentum is)";
     return false;
   }
-  if (spec->regularization_type != "L2") {
-    *err = "regularization_type '" + spec->regularization_type + "' is not supported (L2 only)";
+  if (spec->regularization_type != "L2" && spec->regularization_type != "L1") {
+    *err = "Unknown regularization type: " + spec->regularization_type;  // sgd_solver.cpp:169-171
     return false;
   }
   if (spec->iter_size != 1) {

@@ -200,11 +200,17 @@ struct SegCursor {
   }
 };
 
-// Regularize (L2) + ComputeUpdateValue + Blob::Update for one element, in the
+// Regularize + ComputeUpdateValue + Blob::Update for one element, in the
 // reference's operation order with one rounding per operation:
-//   g = ld*w + g ; h = m*h ; h = lr*g + h ; w = (-1*h) + w
-__device__ __forceinline__ void sgd_element(float g, float& w, float& h, float lr, float ld, float m) {
-  if (ld != 0.f) g = __fadd_rn(__fmul_rn(ld, w), g);
+//   L2: g = ld*w + g          (sgd_solver.cpp:155-160 caffe_axpy(local_decay, data, diff))
+//   L1: g = ld*sign(w) + g    (sgd_solver.cpp:161-168 caffe_cpu_sign into temp_, then caffe_axpy; sign is
+//                              (0 < w) - (w < 0): 0 for +-0 and NaN, math_functions.hpp caffe_sign)
+//   h = m*h ; h = lr*g + h ; w = (-1*h) + w
+__device__ __forceinline__ void sgd_element(float g, float& w, float& h, float lr, float ld, float m, int l1 = 0) {
+  if (ld != 0.f) {
+    const float x = l1 ? static_cast<float>((0.f < w) - (w < 0.f)) : w;
+    g = __fadd_rn(__fmul_rn(ld, x), g);
+  }
   h = __fmul_rn(m, h);
   h = __fadd_rn(__fmul_rn(lr, g), h);
   w = __fadd_rn(__fmul_rn(-1.0f, h), w);
@@ -216,10 +222,10 @@ __device__ __forceinline__ void sgd_vec(const SyncParams& p, SegCursor& c, uint6
   if (i + 3 < c.end[c.k]) {
     const float lr = __fmul_rn(p.rate, c.lr_mult[c.k]);
     const float ld = __fmul_rn(p.weight_decay, c.decay_mult[c.k]);
-    sgd_element(g.x, w.x, h.x, lr, ld, p.momentum);
-    sgd_element(g.y, w.y, h.y, lr, ld, p.momentum);
-    sgd_element(g.z, w.z, h.z, lr, ld, p.momentum);
-    sgd_element(g.w, w.w, h.w, lr, ld, p.momentum);
+    sgd_element(g.x, w.x, h.x, lr, ld, p.momentum, p.l1);
+    sgd_element(g.y, w.y, h.y, lr, ld, p.momentum, p.l1);
+    sgd_element(g.z, w.z, h.z, lr, ld, p.momentum, p.l1);
+    sgd_element(g.w, w.w, h.w, lr, ld, p.momentum, p.l1);
   } else {  // the vector straddles one or more blob boundaries
     const float gg[4] = {g.x, g.y, g.z, g.w};
     float ww[4] = {w.x, w.y, w.z, w.w};
@@ -229,7 +235,7 @@ __device__ __forceinline__ void sgd_vec(const SyncParams& p, SegCursor& c, uint6
     for (int e = 0; e < 4; ++e) {
       while (k < c.nseg - 1 && i + e >= c.end[k]) ++k;
       sgd_element(gg[e], ww[e], hh[e], __fmul_rn(p.rate, c.lr_mult[k]), __fmul_rn(p.weight_decay, c.decay_mult[k]),
-                  p.momentum);
+                  p.momentum, p.l1);
     }
     w = make_float4(ww[0], ww[1], ww[2], ww[3]);
     h = make_float4(hh[0], hh[1], hh[2], hh[3]);

@@ -77,6 +77,7 @@ typedef struct cos_solver_desc {
   const char* snapshot_prefix; /* may be NULL */
   int grad_dtype;              /* COS_GRAD_FP32 | COS_GRAD_BF16 */
   int init_iter;               /* iteration to resume from (0) */
+  int regularization_l1;       /* SolverParameter.regularization_type: 0 = "L2" (default), 1 = "L1" */
 } cos_solver_desc;
 
 /* Gradient producer = Net::ForwardBackward of the reference (solver.cpp:221-223),

@@ -14,7 +14,7 @@ def shard(P, N, p):  # socket_sync_cpu.cpp:46-54
     return (p * P) // N, ((p + 1) * P) // N
 
 
-def step(data, grads, hist, counts, lr_mult, decay_mult, rate, momentum, weight_decay):
+def step(data, grads, hist, counts, lr_mult, decay_mult, rate, momentum, weight_decay, regularization_type="L2"):
     """One Solver::Step on len(data) ranks; returns new (data, hist) lists (inputs untouched)."""
     N, P = len(data), data[0].size
     data = [d.astype(F).copy() for d in data]
@@ -44,7 +44,8 @@ def step(data, grads, hist, counts, lr_mult, decay_mult, rate, momentum, weight_
     ld = np.repeat((F(weight_decay) * np.asarray(decay_mult, F)).astype(F), counts)
     m = F(momentum)
     for r in range(N):
-        gr = np.where(ld != 0, ld * data[r] + g[r], g[r]).astype(F)   # Regularize (saxpy)
+        x = data[r] if regularization_type == "L2" else np.sign(data[r]).astype(F)  # L1: caffe_cpu_sign first
+        gr = np.where(ld != 0, ld * x + g[r], g[r]).astype(F)         # Regularize (saxpy)
         h = (m * hist[r]).astype(F)                                   # axpby = scal ...
         h = (lr * gr + h).astype(F)                                   # ... then axpy
         hist[r] = h

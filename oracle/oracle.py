@@ -51,6 +51,8 @@ def lib():
         L.cos_oracle_reduce_scatter.argtypes = [i32, u64, ppf]
         L.cos_oracle_apply_update.argtypes = [u64, u64, pf, pf, pf, i32, pi64, pf, pf, f32, f32, f32]
         L.cos_oracle_step.argtypes = [i32, u64, ppf, ppf, ppf, i32, pi64, pf, pf, f32, f32, f32]
+        L.cos_oracle_apply_update_ex.argtypes = [u64, u64, pf, pf, pf, i32, pi64, pf, pf, f32, f32, f32, i32]
+        L.cos_oracle_step_ex.argtypes = [i32, u64, ppf, ppf, ppf, i32, pi64, pf, pf, f32, f32, f32, i32]
         L.cos_oracle_round_bf16.argtypes = [u64, pf]
         L.cos_oracle_fill.argtypes = [u64, pf, u64, u64, f32]
         L.cos_oracle_hash.argtypes = [ctypes.c_void_p, u64]
@@ -149,20 +151,21 @@ def _layout(counts, lr_mult, decay_mult):
     return c, lm, dm
 
 
-def apply_update(begin, end, data, diff, hist, counts, lr_mult, decay_mult, rate, momentum, weight_decay):
+def apply_update(begin, end, data, diff, hist, counts, lr_mult, decay_mult, rate, momentum, weight_decay,
+                 regularization_type="L2"):
     c, lm, dm = _layout(counts, lr_mult, decay_mult)
-    lib().cos_oracle_apply_update(begin, end, _pf(data), _pf(diff), _pf(hist), len(c),
-                                  c.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _pf(lm), _pf(dm),
-                                  rate, momentum, weight_decay)
+    lib().cos_oracle_apply_update_ex(begin, end, _pf(data), _pf(diff), _pf(hist), len(c),
+                                     c.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _pf(lm), _pf(dm),
+                                     rate, momentum, weight_decay, int(regularization_type == "L1"))
 
 
-def step(data, diff, hist, counts, lr_mult, decay_mult, rate, momentum, weight_decay):
+def step(data, diff, hist, counts, lr_mult, decay_mult, rate, momentum, weight_decay, regularization_type="L2"):
     """One Solver::Step on len(data) simulated ranks (in place)."""
     c, lm, dm = _layout(counts, lr_mult, decay_mult)
     N, P = len(data), data[0].size
-    lib().cos_oracle_step(N, P, _ppf(data), _ppf(diff), _ppf(hist), len(c),
-                          c.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _pf(lm), _pf(dm),
-                          rate, momentum, weight_decay)
+    lib().cos_oracle_step_ex(N, P, _ppf(data), _ppf(diff), _ppf(hist), len(c),
+                             c.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _pf(lm), _pf(dm),
+                             rate, momentum, weight_decay, int(regularization_type == "L1"))
 
 
 class Simulation:
@@ -173,7 +176,7 @@ class Simulation:
 
     def __init__(self, N, counts, lr_mult=None, decay_mult=None, lr_policy="fixed", base_lr=0.01, gamma=0.1,
                  power=0.75, stepsize=1, stepvalues=(), max_iter=1000, momentum=0.9, weight_decay=0.0005,
-                 seed=1, w_amp=0.05, g_amp=0.01, bf16=False):
+                 seed=1, w_amp=0.05, g_amp=0.01, bf16=False, regularization_type="L2"):
         self.N = N
         self.counts = list(counts)
         self.lr_mult = list(lr_mult) if lr_mult is not None else [1.0] * len(counts)
@@ -183,6 +186,7 @@ class Simulation:
                        stepvalues=tuple(stepvalues), max_iter=max_iter, momentum=momentum,
                        weight_decay=weight_decay)
         self.seed, self.w_amp, self.g_amp, self.bf16 = seed, w_amp, g_amp, bf16
+        self.regularization_type = regularization_type
         w0 = fill(self.P, seed, 0, w_amp)
         self.data = [w0.copy() for _ in range(N)]
         self.hist = [np.zeros(self.P, np.float32) for _ in range(N)]
@@ -203,7 +207,7 @@ class Simulation:
         diff = [np.ascontiguousarray(g, dtype=np.float32).copy() for g in diff]
         rate = self.rate()
         step(self.data, diff, self.hist, self.counts, self.lr_mult, self.decay_mult, rate,
-             self.hp["momentum"], self.hp["weight_decay"])
+             self.hp["momentum"], self.hp["weight_decay"], self.regularization_type)
         self.iter += 1
         return rate
 

@@ -129,8 +129,10 @@ void cos_oracle_reduce_scatter(int N, uint64_t P, float* const* diff) {
 
 /* ApplyUpdate sgd_solver.cpp:102-116 per learnable blob k (ClipGradients is a
  * no-op for clip_gradients < 0, Normalize a no-op for iter_size == 1):
- *   Regularize :145-160 (CPU, L2):  local_decay = weight_decay * decay_mult_k;
- *       if (local_decay) caffe_axpy(local_decay, w, g)        g = ld*w + g
+ *   Regularize :145-172 (CPU):  local_decay = weight_decay * decay_mult_k;
+ *       L2: if (local_decay) caffe_axpy(local_decay, w, g)        g = ld*w + g
+ *       L1: caffe_cpu_sign(w -> temp); caffe_axpy(local_decay, temp, g)
+ *                                                             g = ld*sign(w) + g
  *   ComputeUpdateValue :213-229:    local_rate = rate * lr_mult_k;
  *       caffe_cpu_axpby(local_rate, g, momentum, h)
  *         = cblas_sscal(momentum, h); cblas_saxpy(local_rate, g, h)
@@ -139,11 +141,11 @@ void cos_oracle_reduce_scatter(int N, uint64_t P, float* const* diff) {
  *   Net::Update net.cpp:924 -> Blob::Update blob.cpp:162-179:
  *       caffe_axpy(-1, g, w)                                   w = (-1*g) + w
  * saxpy is taken as the un-fused y[i] = fl(fl(a*x[i]) + y[i]).               */
-void cos_oracle_apply_update(uint64_t begin, uint64_t end, float* data,
-                             float* diff, float* hist, int nblobs,
-                             const int64_t* counts, const float* lr_mult,
-                             const float* decay_mult, float rate,
-                             float momentum, float weight_decay) {
+void cos_oracle_apply_update_ex(uint64_t begin, uint64_t end, float* data,
+                                float* diff, float* hist, int nblobs,
+                                const int64_t* counts, const float* lr_mult,
+                                const float* decay_mult, float rate,
+                                float momentum, float weight_decay, int l1) {
   uint64_t blob_begin = 0;
   for (int k = 0; k < nblobs; ++k) {
     uint64_t blob_end = blob_begin + (uint64_t)counts[k];
@@ -156,7 +158,11 @@ void cos_oracle_apply_update(uint64_t begin, uint64_t end, float* data,
       float w = data[i];
       float h = hist[i];
       if (local_decay != 0.f) {
-        float t = local_decay * w;
+        /* L2 :155-160 caffe_axpy(local_decay, data, diff); L1 :161-168
+         * caffe_cpu_sign(data -> temp_) = (0 < w) - (w < 0)
+         * (math_functions.hpp:113-118 caffe_sign), then the same axpy on temp_ */
+        float x = l1 ? (float)((0.f < w) - (w < 0.f)) : w;
+        float t = local_decay * x;
         g = t + g;
       }
       h = momentum * h;
@@ -177,12 +183,21 @@ void cos_oracle_apply_update(uint64_t begin, uint64_t end, float* data,
   }
 }
 
+void cos_oracle_apply_update(uint64_t begin, uint64_t end, float* data,
+                             float* diff, float* hist, int nblobs,
+                             const int64_t* counts, const float* lr_mult,
+                             const float* decay_mult, float rate,
+                             float momentum, float weight_decay) {
+  cos_oracle_apply_update_ex(begin, end, data, diff, hist, nblobs, counts,
+                             lr_mult, decay_mult, rate, momentum, weight_decay, 0);
+}
+
 /* Solver::Step solver.cpp:194-273 minus ClearParamDiffs/ForwardBackward (the
  * caller provides the local gradients in diff[r]). */
-void cos_oracle_step(int N, uint64_t P, float* const* data, float* const* diff,
-                     float* const* hist, int nblobs, const int64_t* counts,
-                     const float* lr_mult, const float* decay_mult, float rate,
-                     float momentum, float weight_decay) {
+void cos_oracle_step_ex(int N, uint64_t P, float* const* data, float* const* diff,
+                        float* const* hist, int nblobs, const int64_t* counts,
+                        const float* lr_mult, const float* decay_mult, float rate,
+                        float momentum, float weight_decay, int l1) {
   if (N > 1) cos_oracle_all_gather(N, P, data);        /* on_start :214-216 */
   if (N > 1) {                                         /* on_gradients_ready */
     for (int r = 0; r < N; ++r) cos_oracle_scale(N, P, diff[r]);
@@ -191,9 +206,17 @@ void cos_oracle_step(int N, uint64_t P, float* const* data, float* const* diff,
   /* N == 1: LocalCaffeNet in CPU mode installs no sync object at all
    * (CaffeNet.cpp:206-216, syncs_.resize(0)), so no scale is applied. */
   for (int r = 0; r < N; ++r) {                        /* ApplyUpdate :253 */
-    cos_oracle_apply_update(0, P, data[r], diff[r], hist[r], nblobs, counts,
-                            lr_mult, decay_mult, rate, momentum, weight_decay);
+    cos_oracle_apply_update_ex(0, P, data[r], diff[r], hist[r], nblobs, counts,
+                               lr_mult, decay_mult, rate, momentum, weight_decay, l1);
   }
+}
+
+void cos_oracle_step(int N, uint64_t P, float* const* data, float* const* diff,
+                     float* const* hist, int nblobs, const int64_t* counts,
+                     const float* lr_mult, const float* decay_mult, float rate,
+                     float momentum, float weight_decay) {
+  cos_oracle_step_ex(N, P, data, diff, hist, nblobs, counts, lr_mult, decay_mult,
+                     rate, momentum, weight_decay, 0);
 }
 
 void cos_oracle_round_bf16(uint64_t n, float* x) {

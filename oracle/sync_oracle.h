@@ -67,7 +67,7 @@ void cos_oracle_scale(int solver_count, uint64_t P, float* diff);
  * "simultaneously": sends snapshot the already-scaled buffers first. */
 void cos_oracle_reduce_scatter(int N, uint64_t P, float* const* diff);
 
-/* sgd_solver.cpp:102-116 (ApplyUpdate) = Regularize :145-204 (L2 only),
+/* sgd_solver.cpp:102-116 (ApplyUpdate) = Regularize :145-204 (L2; _ex: L2 or L1),
  * ComputeUpdateValue :213-243, Net::Update -> Blob::Update blob.cpp:162-179,
  * on the element range [begin,end) of the flat buffer.  The reference runs the
  * full range [0,P) on every rank; only the owned shard is meaningful. */
@@ -76,6 +76,13 @@ void cos_oracle_apply_update(uint64_t begin, uint64_t end, float* data,
                              const int64_t* counts, const float* lr_mult,
                              const float* decay_mult, float rate,
                              float momentum, float weight_decay);
+
+/* Same with regularization_type selectable: l1 = 0 -> "L2" (:155-160), 1 -> "L1" (:161-168). */
+void cos_oracle_apply_update_ex(uint64_t begin, uint64_t end, float* data,
+                                float* diff, float* hist, int nblobs,
+                                const int64_t* counts, const float* lr_mult,
+                                const float* decay_mult, float rate,
+                                float momentum, float weight_decay, int l1);
 
 /* One complete Solver::Step (solver.cpp:194-273) for N simulated ranks, with
  * the local gradients supplied by the caller in diff[r] (step 2 of SURVEY
@@ -87,6 +94,11 @@ void cos_oracle_step(int N, uint64_t P, float* const* data, float* const* diff,
                      float* const* hist, int nblobs, const int64_t* counts,
                      const float* lr_mult, const float* decay_mult, float rate,
                      float momentum, float weight_decay);
+
+void cos_oracle_step_ex(int N, uint64_t P, float* const* data, float* const* diff,
+                        float* const* hist, int nblobs, const int64_t* counts,
+                        const float* lr_mult, const float* decay_mult, float rate,
+                        float momentum, float weight_decay, int l1);
 
 /* bf16 round-to-nearest-even of an fp32 gradient buffer, in place (config 3:
  * "reference arithmetic applied to bf16-rounded gradient inputs"). */

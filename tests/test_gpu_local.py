@@ -243,3 +243,25 @@ def test_device_fill_is_the_oracles_generator(cos, oracle):
             net.fill(7, 1, 1, 1.0)
     finally:
         net.deallocate()
+
+
+@pytest.mark.parametrize("kernel", [0, 1], ids=["ldg", "tma"])
+def test_l1_regularization_bit_exact(cos, oracle, kernel):
+    """regularization_type: "L1" (sgd_solver.cpp:161-168) on the fused update path, incl. sign(+-0) = 0."""
+    counts, lm, dm = [1021, 7, 64], [1, 2, 1], [1, 0, 0.5]
+    hp = dict(lr_policy="fixed", base_lr=0.01, momentum=0.9, weight_decay=0.004)
+    desc = cos.SolverDesc(counts, lm, dm, regularization_type="L1", **hp)
+    sim = oracle.Simulation(1, counts, lm, dm, seed=17, regularization_type="L1", **hp)
+    sim.data[0][:4] = [0.0, -0.0, 0.5, -0.5]
+    R = Ranks(cos, desc, 1, kernel=kernel)
+    try:
+        R.set_weights([sim.data[0]])
+        R.connect()
+        for t in range(3):
+            g = sim.gradient(0, t)
+            sim.step([g])
+            R.step([g])
+            assert_bits_equal(R.weights(0), sim.data[0], f"L1 weights iter {t}")
+            assert_bits_equal(R.history(0), sim.hist[0], f"L1 history iter {t}")
+    finally:
+        R.close()

@@ -109,6 +109,13 @@ def test_bf16_wire(cos, oracle, N, algo, kernel):
     R.close()
 
 
+@pytest.mark.parametrize("kernel", [0, 2, 4], ids=["ldg", "push", "ll"])
+def test_l1_regularization_multi_rank(cos, oracle, kernel):
+    hp = dict(HP, regularization_type="L1")
+    R, _ = _run_case(cos, oracle, 3, [997, 30, 64], [1, 2, 1], [1, 0, 1], hp, 2, 83, algo=1, kernel=kernel)
+    R.close()
+
+
 def test_first_on_start_reconciles_different_initial_weights(cos, oracle):
     R, _ = _run_case(cos, oracle, 4, [1001, 13], [1, 2], [1, 0], HP, 2, 51, per_rank_init=True, algo=1)
     R.close()

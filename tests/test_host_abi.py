@@ -111,6 +111,13 @@ def test_parser_rejects_what_is_off_the_path(cos, tmp_path):
         cos.parse_solver(str(p))
     with pytest.raises(cos.CosError, match="cannot read solver file"):
         cos.parse_solver(str(tmp_path / "missing.prototxt"))
+    inp = ('net_param { layer { name: "d" type: "Input" top: "data" input_param { shape { dim: 1 dim: 1 dim: 4 dim: 4 } } } '
+           'layer { name: "ip" type: "InnerProduct" bottom: "data" top: "ip" inner_product_param { num_output: 2 } } }')
+    p.write_text('base_lr: 0.1 lr_policy: "fixed" regularization_type: "L1" ' + inp)
+    assert cos.parse_solver(str(p)).regularization_type == "L1"     # sgd_solver.cpp:161-168, on the fused path
+    p.write_text('base_lr: 0.1 lr_policy: "fixed" regularization_type: "L3" ' + inp)
+    with pytest.raises(cos.CosError, match="Unknown regularization type"):
+        cos.parse_solver(str(p))
 
 
 @pytest.mark.skipif(gpu_count() > 0, reason="only meaningful on a GPU-less box")

@@ -217,11 +217,29 @@ def test_c_oracle_agrees_with_independent_numpy_restatement(oracle):
         data = [(rng.randn(P) * 0.05).astype(np.float32) for _ in range(N)]
         hist = [(rng.randn(P) * 0.01).astype(np.float32) for _ in range(N)]
         grads = [(rng.randn(P) * 10 ** rng.uniform(-4, 0)).astype(np.float32) for _ in range(N)]
-        want_d, want_h = NO.step(data, grads, hist, counts, lm, dm, rate, mom, wd)
+        reg = "L1" if trial % 3 == 2 else "L2"  # sgd_solver.cpp:161-168: g += local_decay * sign(w)
+        if reg == "L1":
+            data[0][: min(3, P)] = [0.0, -0.0, 1.0][: min(3, P)]  # sign(+-0) = 0
+        want_d, want_h = NO.step(data, grads, hist, counts, lm, dm, rate, mom, wd, reg)
         d2 = [x.copy() for x in data]
         h2 = [x.copy() for x in hist]
         g2 = [x.copy() for x in grads]
-        oracle.step(d2, g2, h2, counts, lm, dm, rate, mom, wd)
+        oracle.step(d2, g2, h2, counts, lm, dm, rate, mom, wd, reg)
         for r in range(N):
             assert np.array_equal(d2[r].view(np.uint32), want_d[r].view(np.uint32)), (trial, N, r)
             assert np.array_equal(h2[r].view(np.uint32), want_h[r].view(np.uint32)), (trial, N, r)
+
+
+def test_l1_regularization_known_answers(oracle):
+    """Regularize with regularization_type "L1" (sgd_solver.cpp:161-168): diff += local_decay * sign(data), then
+    the usual momentum update.  Hand-computed on exactly representable numbers."""
+    data = np.array([2.0, -4.0, 0.0, -0.0], np.float32)
+    diff = np.array([1.0, 1.0, 1.0, 1.0], np.float32)
+    hist = np.zeros(4, np.float32)
+    # rate 0.5, momentum 0, weight_decay 0.25, lr_mult 1, decay_mult 2 -> local_decay 0.5
+    oracle.apply_update(0, 4, data, diff, hist, [4], [1.0], [2.0], np.float32(0.5), np.float32(0.0), np.float32(0.25), "L1")
+    assert hist.tolist() == [0.75, 0.25, 0.5, 0.5]          # lr * (g + 0.5*sign(w))
+    assert data.tolist() == [1.25, -4.25, -0.5, -0.5]
+    d2, g2, h2 = np.array([2.0, -4.0], np.float32), np.array([1.0, 1.0], np.float32), np.zeros(2, np.float32)
+    oracle.apply_update(0, 2, d2, g2, h2, [2], [1.0], [2.0], np.float32(0.5), np.float32(0.0), np.float32(0.25))  # L2
+    assert h2.tolist() == [1.0, -0.5] and d2.tolist() == [1.0, -3.5]
