@@ -418,6 +418,11 @@ bool CaffeNet::check_status(std::string* err) {
     *err = os.str();
     return false;
   }
+  if (s == 400) {  // fused_sync_sgd_nvls.cu: the zeroing warp never saw an owner finish its reduce phase
+    os << "device-side NVLS reduce phase of a peer did not finish within " << opt_timeout_ms_ << " ms (status 400)";
+    *err = os.str();
+    return false;
+  }
   if (s == 300) {  // fused_sync_sgd_tma.cu: an mbarrier never completed (a bulk copy was lost or a peer died mid-tile)
     os << "device-side TMA pipeline timed out after " << opt_timeout_ms_
        << " ms waiting for a bulk copy to complete (status 300)";

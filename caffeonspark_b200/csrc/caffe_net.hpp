@@ -148,12 +148,15 @@ class CaffeNet {
   int opt_kernel_ = -1;  // -1 auto, 0 LDG/STG pull, 1 TMA bulk-copy pull, 2 push, 3 NVLS (multimem), 4 LL (fence-free)
   int opt_timing_ = 0;   // CUDA events around every launch (cos_net_last_kernel_ms); benchmarks turn it on
   int opt_nvls_ = -1;    // -1 auto (multicast team when world >= 4 and 4P >= nvls_min_bytes), 0 off, 1 on
-  int opt_nvls_unroll_ = 4;     // switch loads in flight per thread
+  int opt_nvls_unroll_ = 1;     // switch loads in flight per thread (1 measured best at N = 2 and N = 8: more only
+                                // unbalances the CTAs, profiles/r02_matrix_large_n8.json)
   int opt_nvls_p2p_ = 0;        // 1: one plain-P2P vector per nvls_unroll switch vectors (link + switch both busy)
   int opt_push_vecs_ = 2;       // push kernel: float4 vectors per thread of the owner phase (sizes the grid)
   int64_t opt_push_max_bytes_ = int64_t(1) << 40;  // AUTO: push kernel below this message size (4P bytes), fp32 wire
   int64_t opt_ll_max_bytes_ = 2 << 20;     // AUTO: LL kernel below this message size (and <= kLLRegionMaxBytes)
-  int64_t opt_nvls_min_bytes_ = 2 << 20;   // AUTO: NVLS kernel at or above this message size when world >= 4
+  int64_t opt_nvls_min_bytes_ = 32 << 20;  // AUTO: NVLS kernel at or above this message size when world >= 4 (N = 8:
+                                           // equal to push at 4-16 MiB, 13-15 % faster from 64 MiB; below, P2P is
+                                           // as fast AND bit-exact)
   int opt_small_grid_ = 0;      // experimental: size the grid by the reduce phase (see CaffeNet::launch)
   int opt_trace_ = 0;           // record %globaltimer at the phase boundaries of CTA 0 (diagnostics)
   int opt_initial_gather_ = 1;  // connect() runs the first on_start() (all-gather of weight shards)

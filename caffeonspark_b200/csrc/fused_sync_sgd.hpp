@@ -14,9 +14,10 @@ namespace cosb {
 
 constexpr int kMaxRanks = 16;
 constexpr int kMaxCtas = 2048;
-// Flag region at the start of every rank's arena: two arrays [kMaxCtas][kMaxRanks]
-// of 32-bit epochs (A = "gradients ready", B = "reads done + weights landed").
-constexpr size_t kFlagBytes = 2ull * kMaxCtas * kMaxRanks * sizeof(uint32_t);
+// Flag region at the start of every rank's arena: three arrays [kMaxCtas][kMaxRanks]
+// of 32-bit words: epochs A = "gradients ready" and B = "reads done + weights landed", and C = per-CTA
+// progress of an owner's reduce phase (NVLS kernel: lets the peers zero diff_ behind the owner's reads).
+constexpr size_t kFlagBytes = 3ull * kMaxCtas * kMaxRanks * sizeof(uint32_t);
 
 enum SyncMode : int {
   kModeLocal = 0,      // world == 1: fused SGD only

@@ -167,31 +167,49 @@ __global__ void __launch_bounds__(kLLThreads, 1) fused_sync_sgd_ll_kernel(const 
   const uint64_t gedge = gslot - kEdgeWords, wedge = wslot - kEdgeWords;
 
   // ---- phase 1: my gradient -> the owners' LL gradient slots [rank] ---------
-  for (int d = 1; d < world; ++d) {
-    int q = rank + d;
-    if (q >= world) q -= world;
-    const ShardRange r = shard_range(p.count, world, q);
-    const uint64_t base = r.lo & ~3ull;
-    uint64_t* dst = p.ll_grad[q] + static_cast<uint64_t>(rank) * gslot;
-    for (uint64_t j = tid; j < r.nvec; j += stride) {
-      const uint64_t i = (r.vec_lo + j) << 2;
-      const float4 v = ld_stream(g + i);
-      if (BF16) {
-        const uint32_t lo2 = static_cast<uint32_t>(float_to_bf16_bits(v.x)) | (static_cast<uint32_t>(float_to_bf16_bits(v.y)) << 16);
-        const uint32_t hi2 = static_cast<uint32_t>(float_to_bf16_bits(v.z)) | (static_cast<uint32_t>(float_to_bf16_bits(v.w)) << 16);
-        st_ll2(dst + ((i - base) >> 1), ll_word(lo2, flag), ll_word(hi2, flag));
-      } else {
-        uint64_t* w = dst + (i - base);
-        st_ll2(w, ll_word(__float_as_uint(v.x), flag), ll_word(__float_as_uint(v.y), flag));
-        st_ll2(w + 2, ll_word(__float_as_uint(v.z), flag), ll_word(__float_as_uint(v.w), flag));
+  // The loads for all N-1 destinations are issued before the first store: one local-memory latency per
+  // iteration instead of N-1.
+  constexpr int D = N - 1;
+  const uint64_t max_nvec = ((p.count + N - 1) / N + 3) >> 2;  // >= nvec of every shard
+  for (uint64_t j = tid; j < max_nvec; j += stride) {
+    float4 v[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      int q = rank + 1 + d;
+      if (q >= N) q -= N;
+      const ShardRange r = shard_range(p.count, N, q);
+      if (j < r.nvec) v[d] = ld_stream(g + ((r.vec_lo + j) << 2));
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      int q = rank + 1 + d;
+      if (q >= N) q -= N;
+      const ShardRange r = shard_range(p.count, N, q);
+      if (j < r.nvec) {
+        const uint64_t i = (r.vec_lo + j) << 2, base = r.lo & ~3ull;
+        uint64_t* dst = p.ll_grad[q] + static_cast<uint64_t>(rank) * gslot;
+        if (BF16) {
+          const uint32_t lo2 = static_cast<uint32_t>(float_to_bf16_bits(v[d].x)) | (static_cast<uint32_t>(float_to_bf16_bits(v[d].y)) << 16);
+          const uint32_t hi2 = static_cast<uint32_t>(float_to_bf16_bits(v[d].z)) | (static_cast<uint32_t>(float_to_bf16_bits(v[d].w)) << 16);
+          st_ll2(dst + ((i - base) >> 1), ll_word(lo2, flag), ll_word(hi2, flag));
+        } else {
+          uint64_t* w = dst + (i - base);
+          st_ll2(w, ll_word(__float_as_uint(v[d].x), flag), ll_word(__float_as_uint(v[d].y), flag));
+          st_ll2(w + 2, ll_word(__float_as_uint(v[d].z), flag), ll_word(__float_as_uint(v[d].w), flag));
+        }
       }
     }
-    if (blockIdx.x == 0) {
+  }
+  if (blockIdx.x == 0) {
+    for (int d = 1; d < world; ++d) {
+      int q = rank + d;
+      if (q >= world) q -= world;
+      const ShardRange r = shard_range(p.count, world, q);
       const uint64_t e = edge_of_thread(r, threadIdx.x);
       if (e != ~0ull) {
         float x = g[e];
         if (BF16) x = bf16_bits_to_float(float_to_bf16_bits(x));
-        st_ll1(dst + gedge + edge_index(r, e), ll_word(__float_as_uint(x), flag));
+        st_ll1(p.ll_grad[q] + static_cast<uint64_t>(rank) * gslot + gedge + edge_index(r, e), ll_word(__float_as_uint(x), flag));
       }
     }
   }
@@ -322,44 +340,46 @@ __global__ void __launch_bounds__(kLLThreads, 1) fused_sync_sgd_ll_kernel(const 
   if (tracer) p.trace[3] = globaltimer_ns();
 
   // ---- phase 3: the peers' updated shards -> my data_ ------------------------
-  for (int d = 1; alive && d < world; ++d) {
-    int q = rank + d;
-    if (q >= world) q -= world;
-    const ShardRange r = shard_range(p.count, world, q);
-    const uint64_t base = r.lo & ~3ull;
-    const uint64_t* src = p.ll_weight[rank] + static_cast<uint64_t>(q) * wslot;
+  // One vector of EVERY peer's shard per round: the 2(N-1) polling loads are in flight together.
+  if (alive) {
     float* wl = p.data[rank];
-    constexpr int kV = 4;  // vectors polled together per thread
-    for (uint64_t j0 = tid; alive && j0 < r.nvec; j0 += stride * kV) {
-      const uint64_t* ptr[kV];
-      uint64_t words[kV][4];
+    for (uint64_t j = tid; alive && j < max_nvec; j += stride) {
+      const uint64_t* ptr[D];
+      uint64_t words[D][4];
+      uint64_t idx[D];
       uint32_t live = 0;
 #pragma unroll
-      for (int v = 0; v < kV; ++v) {
-        const uint64_t j = j0 + static_cast<uint64_t>(v) * stride;
+      for (int d = 0; d < D; ++d) {
+        int q = rank + 1 + d;
+        if (q >= N) q -= N;
+        const ShardRange r = shard_range(p.count, N, q);
         const bool in = j < r.nvec;
-        ptr[v] = src + (in ? (((r.vec_lo + j) << 2) - base) : 0);
-        if (in) live |= 1u << v;
+        idx[d] = (r.vec_lo + j) << 2;
+        ptr[d] = p.ll_weight[rank] + static_cast<uint64_t>(q) * wslot + (in ? idx[d] - (r.lo & ~3ull) : 0);
+        if (in) live |= 1u << d;
       }
-      alive = poll_groups<kV, 4>(ptr, live, flag, poll, q, words);
+      alive = poll_groups<D, 4>(ptr, live, flag, poll, rank, words);
       if (!alive) break;
 #pragma unroll
-      for (int v = 0; v < kV; ++v) {
-        if (live & (1u << v)) {
-          const uint64_t i = (r.vec_lo + j0 + static_cast<uint64_t>(v) * stride) << 2;
-          st_vec(wl + i, make_float4(__uint_as_float(static_cast<uint32_t>(words[v][0])),
-                                     __uint_as_float(static_cast<uint32_t>(words[v][1])),
-                                     __uint_as_float(static_cast<uint32_t>(words[v][2])),
-                                     __uint_as_float(static_cast<uint32_t>(words[v][3]))));
-        }
+      for (int d = 0; d < D; ++d) {
+        if (live & (1u << d))
+          st_vec(wl + idx[d], make_float4(__uint_as_float(static_cast<uint32_t>(words[d][0])),
+                                          __uint_as_float(static_cast<uint32_t>(words[d][1])),
+                                          __uint_as_float(static_cast<uint32_t>(words[d][2])),
+                                          __uint_as_float(static_cast<uint32_t>(words[d][3]))));
       }
     }
     if (alive && blockIdx.x == 0) {
-      const uint64_t e = edge_of_thread(r, threadIdx.x);
-      if (e != ~0ull) {
-        uint32_t u;
-        alive = poll1(src + wedge + edge_index(r, e), flag, poll, q, u);
-        if (alive) wl[e] = __uint_as_float(u);
+      for (int d = 1; alive && d < world; ++d) {
+        int q = rank + d;
+        if (q >= world) q -= world;
+        const ShardRange r = shard_range(p.count, world, q);
+        const uint64_t e = edge_of_thread(r, threadIdx.x);
+        if (e != ~0ull) {
+          uint32_t u;
+          alive = poll1(p.ll_weight[rank] + static_cast<uint64_t>(q) * wslot + wedge + edge_index(r, e), flag, poll, q, u);
+          if (alive) wl[e] = __uint_as_float(u);
+        }
       }
     }
   }

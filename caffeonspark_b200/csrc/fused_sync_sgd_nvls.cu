@@ -20,9 +20,19 @@
 // rounding (north star: 1e-5 relative), not bit for bit; every rank still ends
 // up with IDENTICAL weights because only the owner computes a shard.
 // Each thread keeps UN switch loads + UP x N peer loads + the local w/h loads in
-// flight (all issued before the first use).  Vector j of the shard belongs to
-// CTA (j / blockDim) % gridDim on every rank, so the per-CTA barriers of
-// sync_device.cuh cover the zero phase exactly as in the LDG kernel.
+// flight (all issued before the first use).
+//
+// ClearParamDiffs overlapped with the reduction.  The path is NVLink-bound, HBM
+// is almost idle, yet zeroing diff_ (4P bytes) after barrier B was a serial
+// ~30-70 us tail (profiles/r02_matrix_large_n8.json).  Now 15 of the 16 warps
+// of a CTA reduce; vector j of a shard belongs to CTA (j / 480) % gridDim on
+// every rank.  After each grid-stride iteration the owner's CTA publishes its
+// iteration count into flag array C of every rank (one relaxed store per peer,
+// no fence: it only says "my switch loads of these vectors have RETURNED", i.e.
+// your diff_ has been read).  The 16th warp of the same-numbered CTA on every
+// rank polls those counters in its LOCAL flag memory and zeroes, behind the
+// readers, exactly the vectors that CTA of that owner has consumed.  When the
+// reduction ends, diff_ is already zero; barrier B only waits for the weights.
 #include "fused_sync_sgd.hpp"
 #include "sync_device.cuh"
 
@@ -31,6 +41,11 @@ namespace {
 
 constexpr int kNvlsThreads = 512;
 constexpr int kNvlsMaxSeg = 1024;
+
+constexpr int kWorkThreads = kNvlsThreads - 32;  // warps 0..14 reduce, warp 15 zeroes diff_ behind them
+constexpr uint32_t kIterBits = 16;               // progress word = (epoch << 16) | iterations done (< 65536)
+
+__device__ __forceinline__ void work_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory"); }
 
 template <int UN, int UP, int N>
 __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(const SyncParams p) {
@@ -52,120 +67,181 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
   if (tracer) p.trace[0] = globaltimer_ns();
   const int world = p.world;
   const int rank = p.rank;
-  const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   constexpr int U = UN + UP;
   constexpr int NP = N > 0 ? N : 1;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kWorkThreads;  // vectors per grid-wide round
+  const uint64_t cta_first = static_cast<uint64_t>(blockIdx.x) * kWorkThreads;
+  const uint32_t tag = p.epoch << kIterBits;
 
   // ---- barrier A: every rank has entered the kernel, i.e. its gradients are complete
   if (!cta_barrier(p, 0, &s_abort)) return;
   if (tracer) p.trace[1] = globaltimer_ns();
 
-  SegCursor cur;
-  cur.end = seg_in_smem ? s_end : p.seg_end;
-  cur.lr_mult = seg_in_smem ? s_lr : p.seg_lr_mult;
-  cur.decay_mult = seg_in_smem ? s_dm : p.seg_decay_mult;
-  cur.nseg = p.nseg;
-  cur.k = 0;
-
-  const ShardRange r = shard_range(p.count, world, rank);
-  float* wl = p.data[rank];
-  float* hl = p.hist;
-  const float inv = p.inv_scale;
-  for (uint64_t j0 = tid; j0 < r.nvec; j0 += stride * U) {
-    float4 s[UN > 0 ? UN : 1];
-    float4 x[UP > 0 ? UP : 1][NP];
-    float4 w[U], h[U];
-    // -- issue every load of this iteration
+  if (threadIdx.x < kWorkThreads) {
+    // =================== warps 0..14: reduce + update + broadcast ===================
+    SegCursor cur;
+    cur.end = seg_in_smem ? s_end : p.seg_end;
+    cur.lr_mult = seg_in_smem ? s_lr : p.seg_lr_mult;
+    cur.decay_mult = seg_in_smem ? s_dm : p.seg_decay_mult;
+    cur.nseg = p.nseg;
+    cur.k = 0;
+    const ShardRange r = shard_range(p.count, world, rank);
+    float* wl = p.data[rank];
+    float* hl = p.hist;
+    const float inv = p.inv_scale;
+    const uint64_t tid = cta_first + threadIdx.x;
+    // every work thread of the grid runs the same number of iterations, so the CTA-wide bar.sync below is safe
+    const uint64_t iters = (r.nvec + stride * U - 1) / (stride * U);
+    for (uint64_t it = 0; it < iters; ++it) {
+      const uint64_t j0 = tid + it * stride * U;
+      float4 s[UN > 0 ? UN : 1];
+      float4 x[UP > 0 ? UP : 1][NP];
+      float4 w[U], h[U];
+      // -- issue every load of this iteration
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-      if (j < r.nvec) s[u] = mc_ld_reduce(p.mc_diff + ((r.vec_lo + j) << 2));
-    }
-#pragma unroll
-    for (int u = 0; u < UP; ++u) {
-      const uint64_t j = j0 + static_cast<uint64_t>(UN + u) * stride;
-      if (j < r.nvec) {
-        const uint64_t i = (r.vec_lo + j) << 2;
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-          int src = rank + k;
-          if (src >= NP) src -= NP;
-          x[u][k] = ld_stream(p.diff[src] + i);
-        }
+      for (int u = 0; u < UN; ++u) {
+        const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
+        if (j < r.nvec) s[u] = mc_ld_reduce(p.mc_diff + ((r.vec_lo + j) << 2));
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-      if (j < r.nvec) {
-        const uint64_t i = (r.vec_lo + j) << 2;
-        w[u] = ld_stream(wl + i);
-        h[u] = ld_stream(hl + i);
-      }
-    }
-    // -- consume
+      for (int u = 0; u < UP; ++u) {
+        const uint64_t j = j0 + static_cast<uint64_t>(UN + u) * stride;
+        if (j < r.nvec) {
+          const uint64_t i = (r.vec_lo + j) << 2;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-      if (j < r.nvec) {
-        const uint64_t i = (r.vec_lo + j) << 2;
-        float4 g;
-        if (u < UN) {  // in-switch sum over all ranks, then the 1/N scale
-          g = make_float4(__fmul_rn(inv, s[u].x), __fmul_rn(inv, s[u].y), __fmul_rn(inv, s[u].z),
-                          __fmul_rn(inv, s[u].w));
-        } else {       // reference order: scale first, then r, r+1, ... (mod N)
-          const int q = u - UN;
-          g = make_float4(__fmul_rn(inv, x[q][0].x), __fmul_rn(inv, x[q][0].y), __fmul_rn(inv, x[q][0].z),
-                          __fmul_rn(inv, x[q][0].w));
-#pragma unroll
-          for (int k = 1; k < NP; ++k) {
-            g.x = __fadd_rn(__fmul_rn(inv, x[q][k].x), g.x);
-            g.y = __fadd_rn(__fmul_rn(inv, x[q][k].y), g.y);
-            g.z = __fadd_rn(__fmul_rn(inv, x[q][k].z), g.z);
-            g.w = __fadd_rn(__fmul_rn(inv, x[q][k].w), g.w);
+          for (int k = 0; k < NP; ++k) {
+            int src = rank + k;
+            if (src >= NP) src -= NP;
+            x[u][k] = ld_stream(p.diff[src] + i);
           }
         }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
+        if (j < r.nvec) {
+          const uint64_t i = (r.vec_lo + j) << 2;
+          w[u] = ld_stream(wl + i);
+          h[u] = ld_stream(hl + i);
+        }
+      }
+      // -- consume
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
+        if (j < r.nvec) {
+          const uint64_t i = (r.vec_lo + j) << 2;
+          float4 g;
+          if (u < UN) {  // in-switch sum over all ranks, then the 1/N scale
+            g = make_float4(__fmul_rn(inv, s[u].x), __fmul_rn(inv, s[u].y), __fmul_rn(inv, s[u].z),
+                            __fmul_rn(inv, s[u].w));
+          } else {       // reference order: scale first, then r, r+1, ... (mod N)
+            const int q = u - UN;
+            g = make_float4(__fmul_rn(inv, x[q][0].x), __fmul_rn(inv, x[q][0].y), __fmul_rn(inv, x[q][0].z),
+                            __fmul_rn(inv, x[q][0].w));
+#pragma unroll
+            for (int k = 1; k < NP; ++k) {
+              g.x = __fadd_rn(__fmul_rn(inv, x[q][k].x), g.x);
+              g.y = __fadd_rn(__fmul_rn(inv, x[q][k].y), g.y);
+              g.z = __fadd_rn(__fmul_rn(inv, x[q][k].z), g.z);
+              g.w = __fadd_rn(__fmul_rn(inv, x[q][k].w), g.w);
+            }
+          }
+          cur.seek(i);
+          sgd_vec(p, cur, i, g, w[u], h[u]);
+          st_vec(hl + i, h[u]);
+          if (u < UN) {
+            mc_st(p.mc_data + i, w[u]);  // one store: own data_ and every peer's data_
+          } else {
+            st_vec(wl + i, w[u]);
+#pragma unroll
+            for (int k = 1; k < NP; ++k) {
+              int dst = rank + k;
+              if (dst >= NP) dst -= NP;
+              st_vec(p.data[dst] + i, w[u]);
+            }
+          }
+        }
+      }
+      // -- every gradient load of this CTA's iteration has returned: tell the zeroing warps of all ranks
+      if (p.zero_diff) {
+        work_bar();
+        if (static_cast<int>(threadIdx.x) < world)
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag_slot(p.flags[threadIdx.x], 2, blockIdx.x, rank)),
+                       "r"(tag | static_cast<uint32_t>(it + 1))
+                       : "memory");
+      }
+    }
+    if (blockIdx.x == 0) {  // scalar head / tail of my shard (<= 3 elements each): plain P2P, reference order
+      const uint64_t nhead = r.head_end - r.lo, ntail = r.hi - r.tail_begin;
+      uint64_t i = ~0ull;
+      if (threadIdx.x < nhead) i = r.lo + threadIdx.x;
+      else if (threadIdx.x - nhead < ntail) i = r.tail_begin + (threadIdx.x - nhead);
+      if (i != ~0ull) {
         cur.seek(i);
-        sgd_vec(p, cur, i, g, w[u], h[u]);
-        st_vec(hl + i, h[u]);
-        if (u < UN) {
-          mc_st(p.mc_data + i, w[u]);  // one store: own data_ and every peer's data_
-        } else {
-          st_vec(wl + i, w[u]);
-#pragma unroll
-          for (int k = 1; k < NP; ++k) {
-            int dst = rank + k;
-            if (dst >= NP) dst -= NP;
-            st_vec(p.data[dst] + i, w[u]);
-          }
+        float acc = 0.f;
+        for (int k = 0; k < world; ++k) {
+          int src = rank + k;
+          if (src >= world) src -= world;
+          const float y = __fmul_rn(inv, p.diff[src][i]);
+          acc = (k == 0) ? y : __fadd_rn(y, acc);
+        }
+        float w = wl[i], h = hl[i];
+        sgd_element(acc, w, h, __fmul_rn(p.rate, cur.lr_mult[cur.k]), __fmul_rn(p.weight_decay, cur.decay_mult[cur.k]),
+                    p.momentum, p.l1);
+        hl[i] = h;
+        wl[i] = w;
+        for (int k = 1; k < world; ++k) {
+          int dst = rank + k;
+          if (dst >= world) dst -= world;
+          p.data[dst][i] = w;
         }
       }
     }
-  }
-  if (blockIdx.x == 0) {  // scalar head / tail of my shard (<= 3 elements each): plain P2P, reference order
-    const uint64_t nhead = r.head_end - r.lo, ntail = r.hi - r.tail_begin;
-    uint64_t i = ~0ull;
-    if (threadIdx.x < nhead) i = r.lo + threadIdx.x;
-    else if (threadIdx.x - nhead < ntail) i = r.tail_begin + (threadIdx.x - nhead);
-    if (i != ~0ull) {
-      cur.seek(i);
-      float acc = 0.f;
-      for (int k = 0; k < world; ++k) {
-        int src = rank + k;
-        if (src >= world) src -= world;
-        const float y = __fmul_rn(inv, p.diff[src][i]);
-        acc = (k == 0) ? y : __fadd_rn(y, acc);
+  } else if (p.zero_diff) {
+    // =================== warp 15: ClearParamDiffs behind the readers ===================
+    const int lane = threadIdx.x - kWorkThreads;
+    float* g = const_cast<float*>(p.diff[rank]);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t done[kMaxRanks];  // iterations of owner q (same CTA index) already zeroed here
+    for (int q = 0; q < world; ++q) done[q] = 0;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
+    for (;;) {
+      bool all = true, moved = false;
+      for (int q = 0; q < world; ++q) {
+        const ShardRange rq = shard_range(p.count, world, q);
+        const uint32_t total = static_cast<uint32_t>((rq.nvec + stride * U - 1) / (stride * U));
+        if (done[q] >= total) continue;
+        const uint32_t v = ld_relaxed_sys(flag_slot(p.flags[rank], 2, blockIdx.x, q));
+        const uint32_t upto = (v >> kIterBits) == (tag >> kIterBits) ? (v & ((1u << kIterBits) - 1u)) : 0u;
+        for (uint32_t it = done[q]; it < upto; ++it) {  // this CTA's vectors of iteration `it` of shard q
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint64_t first = cta_first + (static_cast<uint64_t>(it) * U + u) * stride;  // kWorkThreads vectors
+            for (int t = lane; t < kWorkThreads; t += 32) {
+              const uint64_t j = first + t;
+              if (j < rq.nvec) st_vec(g + ((rq.vec_lo + j) << 2), z);
+            }
+          }
+        }
+        if (upto > done[q]) {
+          done[q] = upto;
+          moved = true;
+        }
+        if (done[q] < total) all = false;
       }
-      float w = wl[i], h = hl[i];
-      sgd_element(acc, w, h, __fmul_rn(p.rate, cur.lr_mult[cur.k]), __fmul_rn(p.weight_decay, cur.decay_mult[cur.k]),
-                  p.momentum, p.l1);
-      hl[i] = h;
-      wl[i] = w;
-      for (int k = 1; k < world; ++k) {
-        int dst = rank + k;
-        if (dst >= world) dst -= world;
-        p.data[dst][i] = w;
+      if (all) break;
+      if (!moved) __nanosleep(256);  // leave the load/store unit to the 15 reducing warps
+      if ((++spins & 0xffu) == 0) {
+        if (*reinterpret_cast<volatile int*>(&s_abort)) break;
+        if (globaltimer_ns() - t0 > p.timeout_ns) {  // an owner never finished its reduce phase
+          if (lane == 0) {
+            atomicExch(p.status, 400);
+            *reinterpret_cast<volatile int*>(&s_abort) = 1;
+          }
+          break;
+        }
       }
     }
   }
@@ -175,18 +251,15 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
   if (!cta_barrier(p, 1, &s_abort)) return;
   if (tracer) p.trace[3] = globaltimer_ns();
 
-  // ---- ClearParamDiffs of the next Step, same vector -> CTA partition --------
-  if (p.zero_diff) {
+  // ---- the scalar head / tail elements of every shard (<= 3 each) were read with plain loads by CTA 0 of the
+  // owners: zero them after barrier B
+  if (p.zero_diff && blockIdx.x == 0) {
     float* g = const_cast<float*>(p.diff[rank]);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < world; ++s) {
       const ShardRange q = shard_range(p.count, world, s);
-      for (uint64_t j = tid; j < q.nvec; j += stride) *reinterpret_cast<float4*>(g + ((q.vec_lo + j) << 2)) = z;
-      if (blockIdx.x == 0) {
-        const uint64_t nhead = q.head_end - q.lo, ntail = q.hi - q.tail_begin;
-        if (threadIdx.x < nhead) g[q.lo + threadIdx.x] = 0.f;
-        else if (threadIdx.x - nhead < ntail) g[q.tail_begin + (threadIdx.x - nhead)] = 0.f;
-      }
+      const uint64_t nhead = q.head_end - q.lo, ntail = q.hi - q.tail_begin;
+      if (threadIdx.x < nhead) g[q.lo + threadIdx.x] = 0.f;
+      else if (threadIdx.x - nhead < ntail) g[q.tail_begin + (threadIdx.x - nhead)] = 0.f;
     }
   }
   if (tracer) p.trace[4] = globaltimer_ns();
@@ -218,17 +291,22 @@ cudaError_t launch_fused_sync_sgd_nvls(const SyncParams& p, int grid, cudaStream
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (grid <= 0) grid = sms;  // __launch_bounds__(512, 1): one resident CTA per SM
   if (grid > kMaxCtas) grid = kMaxCtas;
-  uint64_t need = (((p.zero_diff ? p.count : p.count / p.world) >> 2) + kNvlsThreads - 1) / kNvlsThreads;
+  uint64_t need = (((p.count / p.world) >> 2) + kWorkThreads - 1) / kWorkThreads;  // one vector per work thread
   if (need < 1) need = 1;
   if (static_cast<uint64_t>(grid) > need) grid = static_cast<int>(need);
   const size_t smem = p.nseg <= kNvlsMaxSeg ? static_cast<size_t>(p.nseg) * (sizeof(uint64_t) + 2 * sizeof(float)) : 0;
-  const int un = p.nvls_unroll > 0 ? p.nvls_unroll : 4;
+  {  // the per-CTA progress counter has kIterBits bits
+    const uint64_t u = static_cast<uint64_t>((p.nvls_unroll > 0 ? p.nvls_unroll : 1) + (p.nvls_p2p > 0 ? 1 : 0));
+    const uint64_t per_round = static_cast<uint64_t>(grid) * kWorkThreads * u;
+    if ((((p.count / p.world) >> 2) + per_round) / per_round >= (1ull << kIterBits)) return cudaErrorInvalidValue;
+  }
+  const int un = p.nvls_unroll > 0 ? p.nvls_unroll : 1;
   if (p.nvls_p2p <= 0) {
     switch (un) {
-      case 1: return launch_cfg<1, 0, 0>(p, grid, smem, stream);
       case 2: return launch_cfg<2, 0, 0>(p, grid, smem, stream);
+      case 4: return launch_cfg<4, 0, 0>(p, grid, smem, stream);
       case 8: return launch_cfg<8, 0, 0>(p, grid, smem, stream);
-      default: return launch_cfg<4, 0, 0>(p, grid, smem, stream);
+      default: return launch_cfg<1, 0, 0>(p, grid, smem, stream);
     }
   }
   switch (un) {  // one P2P vector per `un` switch vectors

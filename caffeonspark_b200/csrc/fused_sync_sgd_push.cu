@@ -94,40 +94,77 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // ---- phase 1: scatter my gradient into the owners' receive slots ----------
-  constexpr int kU = 4;  // loads in flight per thread
-  for (int d = 1; d < world; ++d) {  // staggered destinations: at any moment the ranks target different peers
-    int q = rank + d;
-    if (q >= world) q -= world;
-    const ShardRange r = shard_range(p.count, world, q);
-    const uint64_t base = r.lo & ~3ull;  // slot element 0 <-> global element base (keeps float4 alignment)
-    uint16_t* dst16 = static_cast<uint16_t*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot;
-    float* dst32 = static_cast<float*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot;
-    for (uint64_t j0 = tid; j0 < r.nvec; j0 += stride * kU) {
-      float4 v[kU];
+  // Destinations are staggered (rank+1, rank+2, ...), so at any moment the ranks target different peers.  For a
+  // compile-time world size the loads for ALL N-1 destinations (x kU vectors) are issued before the first store:
+  // one local-memory latency per iteration instead of N-1 (what a small message is made of at N = 8).
+  if (N > 0) {
+    constexpr int D = N > 0 ? N - 1 : 1;
+    constexpr int kU = D >= 4 ? 1 : (D >= 2 ? 2 : 4);
+    constexpr int NN = N > 0 ? N : 1;  // (this branch is dead for N == 0)
+    const uint64_t max_nvec = ((p.count + NN - 1) / NN + 3) >> 2;  // >= nvec of every shard
+    for (uint64_t j0 = tid; j0 < max_nvec; j0 += stride * kU) {
+      float4 v[kU][D];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-        if (j < r.nvec) v[u] = ld_stream(g + ((r.vec_lo + j) << 2));
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          int q = rank + 1 + d;
+          if (q >= N) q -= N;
+          const ShardRange r = shard_range(p.count, N, q);
+          if (j < r.nvec) v[u][d] = ld_stream(g + ((r.vec_lo + j) << 2));
+        }
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-        if (j < r.nvec) {
-          const uint64_t i = (r.vec_lo + j) << 2;
-          if (BF16) {
-            const uint2 o = pack_bf16x4(v[u]);
-            asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(dst16 + (i - base)), "r"(o.x), "r"(o.y) : "memory");
-          } else {
-            st_vec(dst32 + (i - base), v[u]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          int q = rank + 1 + d;
+          if (q >= N) q -= N;
+          const ShardRange r = shard_range(p.count, N, q);
+          if (j < r.nvec) {
+            const uint64_t i = (r.vec_lo + j) << 2, base = r.lo & ~3ull;  // slot element 0 <-> global element base
+            if (BF16) {
+              const uint2 o = pack_bf16x4(v[u][d]);
+              uint16_t* dst = static_cast<uint16_t*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot + (i - base);
+              asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(dst), "r"(o.x), "r"(o.y) : "memory");
+            } else {
+              st_vec(static_cast<float*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot + (i - base), v[u][d]);
+            }
           }
         }
       }
     }
-    if (blockIdx.x == 0) {
+  } else {
+    for (int d = 1; d < world; ++d) {
+      int q = rank + d;
+      if (q >= world) q -= world;
+      const ShardRange r = shard_range(p.count, world, q);
+      const uint64_t base = r.lo & ~3ull;
+      for (uint64_t j = tid; j < r.nvec; j += stride) {
+        const uint64_t i = (r.vec_lo + j) << 2;
+        const float4 v = ld_stream(g + i);
+        if (BF16) {
+          const uint2 o = pack_bf16x4(v);
+          uint16_t* dst = static_cast<uint16_t*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot + (i - base);
+          asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(dst), "r"(o.x), "r"(o.y) : "memory");
+        } else {
+          st_vec(static_cast<float*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot + (i - base), v);
+        }
+      }
+    }
+  }
+  if (blockIdx.x == 0) {  // scalar head / tail elements of every foreign shard
+    for (int d = 1; d < world; ++d) {
+      int q = rank + d;
+      if (q >= world) q -= world;
+      const ShardRange r = shard_range(p.count, world, q);
+      const uint64_t base = r.lo & ~3ull;
       const uint64_t i = edge_element(r, threadIdx.x);
       if (i != ~0ull) {
-        if (BF16) dst16[i - base] = float_to_bf16_bits(g[i]);
-        else dst32[i - base] = g[i];
+        if (BF16) (static_cast<uint16_t*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot)[i - base] = float_to_bf16_bits(g[i]);
+        else (static_cast<float*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot)[i - base] = g[i];
       }
     }
   }
@@ -296,12 +333,12 @@ cudaError_t launch_fused_sync_sgd_push(const SyncParams& p, int grid, int block,
   if (vecs_per_thread <= 0) vecs_per_thread = 2;
   const int cap = 2 * 148 < kMaxCtas ? 2 * 148 : kMaxCtas;
   if (grid <= 0) {
-    // sized by the owner's shard: vecs_per_thread vectors per thread in phase 2 (phase 1 then moves
-    // (N-1) x that); few CTAs = few flags, many CTAs = bandwidth.  Depends only on (P, N): identical on
-    // every rank, as the per-CTA barriers need.
-    const uint64_t shard_vecs = (p.count / p.world) >> 2;
+    // sized by the scatter phase, which moves (N-1)/N of the buffer: vecs_per_thread of those vectors per thread
+    // (the owner phase then has 1/(N-1) of that per thread).  Few CTAs = few flags, many CTAs = bandwidth.
+    // Depends only on (P, N): identical on every rank, as the per-CTA barriers need.
+    const uint64_t vecs = (p.count - p.count / p.world) >> 2;
     const uint64_t per_cta = static_cast<uint64_t>(block) * vecs_per_thread;
-    uint64_t need = (shard_vecs + per_cta - 1) / per_cta;
+    uint64_t need = (vecs + per_cta - 1) / per_cta;
     if (need < 1) need = 1;
     grid = static_cast<int>(need > static_cast<uint64_t>(cap) ? cap : need);
   }

@@ -213,14 +213,16 @@ COS_API int cos_net_synchronize(cos_net* net);
 /* Options: "algo" (COS_ALGO_*), "zero_diff" (0/1, default 1),
  * "grid" (CTAs, 0 = auto), "block" (threads, 0 = auto), "kernel" (-1 = auto,
  * 0 = LDG/STG pull kernel, 1 = TMA bulk-copy pull pipeline, 2 = push kernel
- * (stores only, bf16 cast in registers), 3 = NVLS multimem kernel),
- * "barrier_timeout_ms", "one_shot_max_bytes", "push_max_bytes" / "nvls_min_bytes"
- * (AUTO thresholds on the message size 4P), "push_vecs" (push kernel grid sizing),
+ * (stores only, bf16 cast in registers), 3 = NVLS multimem kernel, 4 = LL kernel
+ * (flag-in-data words, no barrier / fence; small nets, cluster_size <= 8)),
+ * "barrier_timeout_ms", "one_shot_max_bytes", "ll_max_bytes" / "push_max_bytes" /
+ * "nvls_min_bytes" (AUTO thresholds on the message size 4P), "push_vecs" (push / LL
+ * kernel grid sizing),
  * "timing" (CUDA events around each launch, default 0), "initial_gather" (0 =
  * connect() skips the first on_start(); the caller then runs
  * cos_net_all_gather_weights itself), "nvls" (-1 = auto: join an NVSwitch
  * multicast team at connect() when cluster_size >= 4, the wire is fp32 and
- * 4P >= nvls_min_bytes; 0 = never; 1 = always try.  The in-switch sum matches the
+ * 4P >= nvls_min_bytes (32 MiB); 0 = never; 1 = always try.  The in-switch sum matches the
  * reference to 1e-5, not bitwise: set 0 for bit-exact runs), "nvls_unroll",
  * "nvls_p2p" (share of plain-P2P vectors in the NVLS kernel), "train_pipeline"
  * (1 = cos_net_train returns once its batch has left host memory; 0 = after the

@@ -44,6 +44,10 @@ def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0, nvls=F
         counts, lm, dm = ([500, 20, 25000, 50, 400000, 500, 5000, 10] if not shared_gpu else
                           [500, 20, 2500, 50, 4000, 500, 5000, 10]), [1, 2] * 4, [1, 1] * 4
         hp = dict(lr_policy="inv", base_lr=0.01, gamma=0.0001, power=0.75, momentum=0.9, weight_decay=0.0005)
+        opts = dict(opts or {})
+        if "_counts" in opts:  # a bigger layout (several grid-stride rounds per CTA)
+            counts = opts.pop("_counts")
+            lm, dm = [1, 2] * (len(counts) // 2), [1, 0] * (len(counts) // 2)
         desc = C.SolverDesc(counts, lm, dm, grad_dtype="bf16" if bf16 else "fp32", **hp)
         sim = O.Simulation(world, counts, lm, dm, seed=77, bf16=bf16, **hp)
         cl = Cluster(desc, rank=rank, world=world, device=dev)
@@ -79,6 +83,7 @@ def _worker(rank, world, port, algo, bf16, q, shared_gpu=False, kernel=0, nvls=F
                                            sim.consistent_weights().view(np.uint32))
                 ok = ok and np.array_equal(to_host(net.history())[o:o + s].view(np.uint32),
                                            sim.consistent_history()[o:o + s].view(np.uint32))
+            ok = ok and not bool(net.diff().any())  # ClearParamDiffs folded into the kernel (every variant)
         q.put((rank, bool(ok), int(net.get_option("nvls_active")), float(net.last_kernel_ms())))
         assert net.sync()
         net.deallocate()
@@ -133,6 +138,29 @@ def test_nvls_two_shot_within_tolerance(cos, oracle, unroll, p2p):
     active = {a for _, _, a, _ in res}
     assert len(active) == 1, "ranks disagree on whether NVLS is active"
     print("NVLS active:", active)
+
+
+@pytest.mark.skipif(gpu_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("kernel,nvls,bf16", [(3, True, False), (2, False, False), (2, False, True), (1, False, False)])
+def test_multi_round_layout_one_process_per_gpu(cos, oracle, kernel, nvls, bf16):
+    """12 MB layout: every CTA runs several grid-stride rounds, so the NVLS kernel's zeroing warp follows the
+    owners' progress counters over many iterations (and the push / TMA kernels loop).  diff_ must end up zero and
+    the weights must match the oracle (bit-exact for P2P, 1e-5 for the in-switch sum)."""
+    import torch.multiprocessing as mp
+    world = min(gpu_count(), 8)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    opts = {"_counts": [3000000, 1000, 7, 13]}
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 1, bf16, q, False, kernel, nvls, opts)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert all(ok for _, ok, _, _ in res), res
 
 
 @pytest.mark.skipif(gpu_count() < 1, reason="needs a GPU")
