@@ -262,7 +262,8 @@ int CaffeNet::resolved_algo() const {
 // Kernel variant (0 LDG/STG pull, 1 TMA bulk-copy pull, 2 push, 3 NVLS).  Depends only on (world, P, wire
 // dtype, options, NVLS team) -- all identical on every rank -- so every rank resolves the same variant, which
 // the per-CTA barriers require.  AUTO, from the B200 measurements under profiles/:
-//   * N >= 4, fp32 wire, multicast team up, 4P >= nvls_min_bytes: NVLS (half the NVLink bytes of P2P);
+//   * N >= 6, fp32 wire, multicast team up, 4P >= nvls_min_bytes: NVLS (4P(1+1/N) NVLink bytes per direction
+//     instead of 8P(N-1)/N; measured 15-20 % faster than push at N = 8, estimated break-even at N ~ 5);
 //   * 4P < ll_max_bytes (N <= 8): LL -- flag-in-data words, no barrier, no fence (latency-bound sizes);
 //   * otherwise push (stores only; the bf16 cast costs no extra pass; measured >= the TMA pull pipeline at
 //     every size on B200), the TMA pull pipeline above push_max_bytes.
@@ -280,7 +281,7 @@ int CaffeNet::resolved_kernel() const {
   if (opt_kernel_ == 4 && ll_ok) return 4;
   if (world_ == 1) return 0;
   if (algo != kModeTwoShot) return bytes >= (2 << 20) ? 1 : 0;
-  if (nvls_ok && (opt_nvls_ == 1 || (world_ >= 4 && bytes >= opt_nvls_min_bytes_))) return 3;
+  if (nvls_ok && (opt_nvls_ == 1 || (world_ >= kNvlsAutoMinWorld && bytes >= opt_nvls_min_bytes_))) return 3;
   if (ll_ok && bytes < opt_ll_max_bytes_) return 4;
   if (push_ok && (!fp32 || bytes < opt_push_max_bytes_)) return 2;
   return bytes >= (2 << 20) ? 1 : 0;
@@ -905,9 +906,9 @@ bool NvlinkCaffeNet::connect(const std::vector<std::string>& addresses, std::str
     peer_llw_[peer] = ll_grad_stride_ ? reinterpret_cast<uint64_t*>(base + off_llw_) : nullptr;
   }
   connected_ = true;
-  // NVLS multicast team: on request, or by default where it pays (N >= 4, message >= nvls_min_bytes, fp32 wire).
+  // NVLS multicast team: on request, or by default where it pays (N >= 6, message >= nvls_min_bytes, fp32 wire).
   // The decision uses only values that are identical on every rank.
-  const bool want_nvls = opt_nvls_ == 1 || (opt_nvls_ < 0 && world_ >= 4 && spec_.grad_dtype == COS_GRAD_FP32 &&
+  const bool want_nvls = opt_nvls_ == 1 || (opt_nvls_ < 0 && world_ >= kNvlsAutoMinWorld && spec_.grad_dtype == COS_GRAD_FP32 &&
                                             static_cast<int64_t>(count_ * sizeof(float)) >= opt_nvls_min_bytes_);
   if (want_nvls) setup_nvls(timeout);
   // everyone has mapped everyone; then the first on_start(): all-gather of the

@@ -28,6 +28,11 @@
 
 namespace cosb {
 
+// AUTO uses the NVLS kernel from this world size on.  NVLink bytes per direction: NVLS 4P(1+1/N), P2P 8P(N-1)/N, but
+// multimem traffic carries ~30 % protocol overhead vs ~13 % for plain stores (NVML raw vs payload counters): measured
+// at CaffeNet size NVLS wins by 15-20 % at N = 8 and loses at N = 2; the N = 4 point of round 1 was a tie / small loss.
+constexpr int kNvlsAutoMinWorld = 6;
+
 class CaffeNet {
  public:
   // JniCaffeNet.cpp:41-64 dispatch.  Returns nullptr and sets *err on failure.
@@ -147,14 +152,14 @@ class CaffeNet {
   int opt_grid_ = 0, opt_block_ = 0;
   int opt_kernel_ = -1;  // -1 auto, 0 LDG/STG pull, 1 TMA bulk-copy pull, 2 push, 3 NVLS (multimem), 4 LL (fence-free)
   int opt_timing_ = 0;   // CUDA events around every launch (cos_net_last_kernel_ms); benchmarks turn it on
-  int opt_nvls_ = -1;    // -1 auto (multicast team when world >= 4 and 4P >= nvls_min_bytes), 0 off, 1 on
+  int opt_nvls_ = -1;    // -1 auto (multicast team when world >= kNvlsAutoMinWorld and 4P >= nvls_min_bytes), 0 off, 1 on
   int opt_nvls_unroll_ = 1;     // switch loads in flight per thread (1 measured best at N = 2 and N = 8: more only
                                 // unbalances the CTAs, profiles/r02_matrix_large_n8.json)
   int opt_nvls_p2p_ = 0;        // 1: one plain-P2P vector per nvls_unroll switch vectors (link + switch both busy)
   int opt_push_vecs_ = 2;       // push kernel: float4 vectors per thread of the owner phase (sizes the grid)
   int64_t opt_push_max_bytes_ = int64_t(1) << 40;  // AUTO: push kernel below this message size (4P bytes), fp32 wire
   int64_t opt_ll_max_bytes_ = 2 << 20;     // AUTO: LL kernel below this message size (and <= kLLRegionMaxBytes)
-  int64_t opt_nvls_min_bytes_ = 32 << 20;  // AUTO: NVLS kernel at or above this message size when world >= 4 (N = 8:
+  int64_t opt_nvls_min_bytes_ = 32 << 20;  // AUTO: NVLS kernel at or above this message size when world >= 6 (N = 8:
                                            // equal to push at 4-16 MiB, 13-15 % faster from 64 MiB; below, P2P is
                                            // as fast AND bit-exact)
   int opt_small_grid_ = 0;      // experimental: size the grid by the reduce phase (see CaffeNet::launch)

@@ -221,7 +221,7 @@ COS_API int cos_net_synchronize(cos_net* net);
  * "timing" (CUDA events around each launch, default 0), "initial_gather" (0 =
  * connect() skips the first on_start(); the caller then runs
  * cos_net_all_gather_weights itself), "nvls" (-1 = auto: join an NVSwitch
- * multicast team at connect() when cluster_size >= 4, the wire is fp32 and
+ * multicast team at connect() when cluster_size >= 6, the wire is fp32 and
  * 4P >= nvls_min_bytes (32 MiB); 0 = never; 1 = always try.  The in-switch sum matches the
  * reference to 1e-5, not bitwise: set 0 for bit-exact runs), "nvls_unroll",
  * "nvls_p2p" (share of plain-P2P vectors in the NVLS kernel), "train_pipeline"
