@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
     const float inv = p.inv_scale;
     const uint64_t tid = cta_first + threadIdx.x;
     // every work thread of the grid runs the same number of iterations, so the CTA-wide bar.sync below is safe
-    const uint64_t iters = (r.nvec + stride * U - 1) / (stride * U);
+    const uint64_t iters = (r.off + r.nvec + stride * U - 1) / (stride * U);  // over the 512-byte aligned index space
     for (uint64_t it = 0; it < iters; ++it) {
       const uint64_t j0 = tid + it * stride * U;
       float4 s[UN > 0 ? UN : 1];
@@ -100,14 +100,13 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
       // -- issue every load of this iteration
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-        if (j < r.nvec) s[u] = mc_ld_reduce(p.mc_diff + ((r.vec_lo + j) << 2));
+        const uint64_t i = vec_elem(r, j0 + static_cast<uint64_t>(u) * stride);
+        if (i != ~0ull) s[u] = mc_ld_reduce(p.mc_diff + i);
       }
 #pragma unroll
       for (int u = 0; u < UP; ++u) {
-        const uint64_t j = j0 + static_cast<uint64_t>(UN + u) * stride;
-        if (j < r.nvec) {
-          const uint64_t i = (r.vec_lo + j) << 2;
+        const uint64_t i = vec_elem(r, j0 + static_cast<uint64_t>(UN + u) * stride);
+        if (i != ~0ull) {
 #pragma unroll
           for (int k = 0; k < NP; ++k) {
             int src = rank + k;
@@ -118,9 +117,8 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-        if (j < r.nvec) {
-          const uint64_t i = (r.vec_lo + j) << 2;
+        const uint64_t i = vec_elem(r, j0 + static_cast<uint64_t>(u) * stride);
+        if (i != ~0ull) {
           w[u] = ld_stream(wl + i);
           h[u] = ld_stream(hl + i);
         }
@@ -128,9 +126,8 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
       // -- consume
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint64_t j = j0 + static_cast<uint64_t>(u) * stride;
-        if (j < r.nvec) {
-          const uint64_t i = (r.vec_lo + j) << 2;
+        const uint64_t i = vec_elem(r, j0 + static_cast<uint64_t>(u) * stride);
+        if (i != ~0ull) {
           float4 g;
           if (u < UN) {  // in-switch sum over all ranks, then the 1/N scale
             g = make_float4(__fmul_rn(inv, s[u].x), __fmul_rn(inv, s[u].y), __fmul_rn(inv, s[u].z),
@@ -211,7 +208,7 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
       bool all = true, moved = false;
       for (int q = 0; q < world; ++q) {
         const ShardRange rq = shard_range(p.count, world, q);
-        const uint32_t total = static_cast<uint32_t>((rq.nvec + stride * U - 1) / (stride * U));
+        const uint32_t total = static_cast<uint32_t>((rq.off + rq.nvec + stride * U - 1) / (stride * U));
         if (done[q] >= total) continue;
         const uint32_t v = ld_relaxed_sys(flag_slot(p.flags[rank], 2, blockIdx.x, q));
         const uint32_t upto = (v >> kIterBits) == (tag >> kIterBits) ? (v & ((1u << kIterBits) - 1u)) : 0u;
@@ -220,8 +217,8 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) fused_sync_sgd_nvls_kernel(co
           for (int u = 0; u < U; ++u) {
             const uint64_t first = cta_first + (static_cast<uint64_t>(it) * U + u) * stride;  // kWorkThreads vectors
             for (int t = lane; t < kWorkThreads; t += 32) {
-              const uint64_t j = first + t;
-              if (j < rq.nvec) st_vec(g + ((rq.vec_lo + j) << 2), z);
+              const uint64_t i = vec_elem(rq, first + t);
+              if (i != ~0ull) st_vec(g + i, z);
             }
           }
         }
@@ -298,7 +295,7 @@ cudaError_t launch_fused_sync_sgd_nvls(const SyncParams& p, int grid, cudaStream
   {  // the per-CTA progress counter has kIterBits bits
     const uint64_t u = static_cast<uint64_t>((p.nvls_unroll > 0 ? p.nvls_unroll : 1) + (p.nvls_p2p > 0 ? 1 : 0));
     const uint64_t per_round = static_cast<uint64_t>(grid) * kWorkThreads * u;
-    if ((((p.count / p.world) >> 2) + per_round) / per_round >= (1ull << kIterBits)) return cudaErrorInvalidValue;
+    if ((((p.count / p.world) >> 2) + 64 + per_round) / per_round >= (1ull << kIterBits)) return cudaErrorInvalidValue;
   }
   const int un = p.nvls_unroll > 0 ? p.nvls_unroll : 1;
   if (p.nvls_p2p <= 0) {

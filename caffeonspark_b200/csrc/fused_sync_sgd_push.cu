@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
     constexpr int D = N > 0 ? N - 1 : 1;
     constexpr int kU = D >= 4 ? 1 : (D >= 2 ? 2 : 4);
     constexpr int NN = N > 0 ? N : 1;  // (this branch is dead for N == 0)
-    const uint64_t max_nvec = ((p.count + NN - 1) / NN + 3) >> 2;  // >= nvec of every shard
+    const uint64_t max_nvec = (((p.count + NN - 1) / NN + 3) >> 2) + 32;  // >= off + nvec of every shard
     for (uint64_t j0 = tid; j0 < max_nvec; j0 += stride * kU) {
       float4 v[kU][D];
 #pragma unroll
@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
           int q = rank + 1 + d;
           if (q >= N) q -= N;
           const ShardRange r = shard_range(p.count, N, q);
-          if (j < r.nvec) v[u][d] = ld_stream(g + ((r.vec_lo + j) << 2));
+          const uint64_t i = vec_elem(r, j);
+          if (i != ~0ull) v[u][d] = ld_stream(g + i);
         }
       }
 #pragma unroll
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
           int q = rank + 1 + d;
           if (q >= N) q -= N;
           const ShardRange r = shard_range(p.count, N, q);
-          if (j < r.nvec) {
-            const uint64_t i = (r.vec_lo + j) << 2, base = r.lo & ~3ull;  // slot element 0 <-> global element base
+          const uint64_t i = vec_elem(r, j), base = r.vec_base << 2;  // slot element 0 <-> global element base
+          if (i != ~0ull) {
             if (BF16) {
               const uint2 o = pack_bf16x4(v[u][d]);
               uint16_t* dst = static_cast<uint16_t*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot + (i - base);
@@ -141,9 +142,10 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
       int q = rank + d;
       if (q >= world) q -= world;
       const ShardRange r = shard_range(p.count, world, q);
-      const uint64_t base = r.lo & ~3ull;
-      for (uint64_t j = tid; j < r.nvec; j += stride) {
-        const uint64_t i = (r.vec_lo + j) << 2;
+      const uint64_t base = r.vec_base << 2;
+      for (uint64_t j = tid; j < r.off + r.nvec; j += stride) {
+        const uint64_t i = vec_elem(r, j);
+        if (i == ~0ull) continue;
         const float4 v = ld_stream(g + i);
         if (BF16) {
           const uint2 o = pack_bf16x4(v);
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
       int q = rank + d;
       if (q >= world) q -= world;
       const ShardRange r = shard_range(p.count, world, q);
-      const uint64_t base = r.lo & ~3ull;
+      const uint64_t base = r.vec_base << 2;
       const uint64_t i = edge_element(r, threadIdx.x);
       if (i != ~0ull) {
         if (BF16) (static_cast<uint16_t*>(p.recv[q]) + static_cast<uint64_t>(rank) * slot)[i - base] = float_to_bf16_bits(g[i]);
@@ -177,7 +179,10 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
       int q = rank + d;
       if (q >= world) q -= world;
       const ShardRange r = shard_range(p.count, world, q);
-      for (uint64_t j = tid; j < r.nvec; j += stride) st_vec(g + ((r.vec_lo + j) << 2), z4);
+      for (uint64_t j = tid; j < r.off + r.nvec; j += stride) {
+        const uint64_t i = vec_elem(r, j);
+        if (i != ~0ull) st_vec(g + i, z4);
+      }
       if (blockIdx.x == 0) {
         const uint64_t i = edge_element(r, threadIdx.x);
         if (i != ~0ull) g[i] = 0.f;
@@ -196,13 +201,18 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
   cur.k = 0;
   {
     const ShardRange r = shard_range(p.count, world, rank);
-    const uint64_t base = r.lo & ~3ull;
+    const uint64_t base = r.vec_base << 2;
     float* wl = p.data[rank];
     float* hl = p.hist;
     const float inv = p.inv_scale;
-    if (tid < r.nvec) cur.seek((r.vec_lo + tid) << 2);
-    for (uint64_t j = tid; j < r.nvec; j += stride) {
-      const uint64_t i = (r.vec_lo + j) << 2;
+    bool sought = false;
+    for (uint64_t j = tid; j < r.off + r.nvec; j += stride) {
+      const uint64_t i = vec_elem(r, j);
+      if (i == ~0ull) continue;
+      if (!sought) {
+        cur.seek(i);
+        sought = true;
+      }
       constexpr int M = N > 0 ? N : 1;
       float4 x[M];
       x[0] = ld_stream(g + i);
@@ -300,7 +310,10 @@ __global__ void __launch_bounds__(kPushThreads, 2) fused_sync_sgd_push_kernel(co
   cta_signal(p, 1);
   if (zero) {  // own shard of diff_: read by this CTA in phase 2 only
     const ShardRange r = shard_range(p.count, world, rank);
-    for (uint64_t j = tid; j < r.nvec; j += stride) st_vec(g + ((r.vec_lo + j) << 2), z4);
+    for (uint64_t j = tid; j < r.off + r.nvec; j += stride) {
+      const uint64_t i = vec_elem(r, j);
+      if (i != ~0ull) st_vec(g + i, z4);
+    }
     if (blockIdx.x == 0) {
       const uint64_t i = edge_element(r, threadIdx.x);
       if (i != ~0ull) g[i] = 0.f;
@@ -321,7 +334,7 @@ cudaError_t launch_push_n(const SyncParams& p, int grid, int block, size_t smem,
 
 uint64_t push_recv_stride(uint64_t count, int world) {
   const uint64_t max_shard = (count + world - 1) / world;  // shard sizes differ by at most one element
-  return (max_shard + 4 + 31) / 32 * 32;                   // + up to 3 elements of alignment slack in front
+  return (max_shard + 4 * 32 + 8 + 31) / 32 * 32;          // + up to 32 vectors of 512-byte alignment slack in front
 }
 
 cudaError_t launch_fused_sync_sgd_push(const SyncParams& p, int grid, int block, int vecs_per_thread,

@@ -157,7 +157,19 @@ struct ShardRange {
   uint64_t nvec;          // number of float4 vectors fully inside
   uint64_t head_end;      // [lo, head_end) scalar head
   uint64_t tail_begin;    // [tail_begin, hi) scalar tail
+  // 512-byte aligned iteration space (push / NVLS kernels): thread index a = tid + k*stride addresses vector
+  // vec_base + a, valid for off <= a < off + nvec.  vec_base is a multiple of 32 vectors, so every warp's 32 float4
+  // cover exactly four 128-byte lines of data_ / diff_ / the receive slot -- with the plain j = tid + k*stride walk
+  // a shard that starts mid-line (CaffeNet: every shard but one) makes EVERY warp access straddle lines: partial
+  // sectors over NVLink (+3 % payload counted by NVML) and 7 % more time at N = 2 (422 vs 395 us).
+  uint64_t vec_base;      // (lo / 4) rounded down to a multiple of 32
+  uint64_t off;           // vec_lo - vec_base, 0..32
 };
+
+// aligned index a -> element index of its vector in shard r, or ~0 when a is outside the shard's vector body
+__device__ __forceinline__ uint64_t vec_elem(const ShardRange& r, uint64_t a) {
+  return (a >= r.off && a - r.off < r.nvec) ? ((r.vec_base + a) << 2) : ~0ull;
+}
 
 // socket_sync_cpu.cpp:46-54 chunk(): multiply first, then divide, in 64 bit.
 __device__ __forceinline__ ShardRange shard_range(uint64_t count, int world, int s) {
@@ -176,6 +188,8 @@ __device__ __forceinline__ ShardRange shard_range(uint64_t count, int world, int
     r.head_end = r.hi;  // everything scalar
     r.tail_begin = r.hi;
   }
+  r.vec_base = (r.lo >> 2) & ~31ull;
+  r.off = r.vec_lo - r.vec_base;
   return r;
 }
 
