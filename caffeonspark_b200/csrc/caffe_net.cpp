@@ -345,19 +345,7 @@ bool CaffeNet::launch(int mode, cudaStream_t stream, std::string* err) {
   }
   if (world_ > 1) p.epoch = ++epoch_;
   if (opt_timing_) COS_RT(cudaEventRecord(ev_start_, stream));
-  int grid = opt_grid_;
-  if (grid == 0 && opt_small_grid_ && world_ > 1 && mode == kModeTwoShot) {
-    // EXPERIMENTAL (off by default, to be measured in round 2): the default grid is sized by the zero / cast
-    // phases, which puts e.g. 211 CTAs through two cross-GPU barriers for LeNet although the reduce phase only
-    // has work for 27.  Size it by the reduce phase, letting the zero phase loop up to 4x per thread.
-    const uint64_t block = opt_block_ > 0 ? opt_block_ : 512;
-    const uint64_t shard_vecs = (count_ / world_) >> 2, total_vecs = count_ >> 2;
-    uint64_t need = (shard_vecs + block - 1) / block;
-    const uint64_t need_zero = (total_vecs + 4 * block - 1) / (4 * block);
-    if (need_zero > need) need = need_zero;
-    const uint64_t cap = static_cast<uint64_t>(default_sync_grid(device_));
-    grid = static_cast<int>(need < 1 ? 1 : (need > cap ? cap : need));
-  }
+  const int grid = opt_grid_;
   const int kern = (mode == kModeAllGather) ? 0 : resolved_kernel();
   cudaError_t e;
   switch (kern) {
@@ -588,7 +576,6 @@ bool CaffeNet::set_option(const std::string& name, int64_t v, std::string* err) 
   else if (name == "iter") { iter_ = static_cast<int>(v); }
   else if (name == "initial_gather") opt_initial_gather_ = v != 0;
   else if (name == "trace") opt_trace_ = v != 0;
-  else if (name == "small_grid") opt_small_grid_ = v != 0;
   else if (name == "train_pipeline") opt_train_pipeline_ = v != 0;
   else {
     *err = "unknown option '" + name + "'";
@@ -617,7 +604,6 @@ int64_t CaffeNet::get_option(const std::string& name) const {
   if (name == "barrier_timeout_ms") return opt_timeout_ms_;
   if (name == "one_shot_max_bytes") return opt_one_shot_max_bytes_;
   if (name == "initial_gather") return opt_initial_gather_;
-  if (name == "small_grid") return opt_small_grid_;
   if (name == "train_pipeline") return opt_train_pipeline_;
   if (name.compare(0, 6, "trace_") == 0 && name.size() >= 7 && name.size() <= 8) {  // trace_0 .. trace_12
     const int k = atoi(name.c_str() + 6);

@@ -162,7 +162,6 @@ class CaffeNet {
   int64_t opt_nvls_min_bytes_ = 32 << 20;  // AUTO: NVLS kernel at or above this message size when world >= 6 (N = 8:
                                            // equal to push at 4-16 MiB, 13-15 % faster from 64 MiB; below, P2P is
                                            // as fast AND bit-exact)
-  int opt_small_grid_ = 0;      // experimental: size the grid by the reduce phase (see CaffeNet::launch)
   int opt_trace_ = 0;           // record %globaltimer at the phase boundaries of CTA 0 (diagnostics)
   int opt_initial_gather_ = 1;  // connect() runs the first on_start() (all-gather of weight shards)
   int64_t opt_timeout_ms_ = 20000;

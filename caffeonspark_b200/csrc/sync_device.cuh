@@ -22,16 +22,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // streaming 128-bit load that does not allocate in L1 (each element is read once)
 __device__ __forceinline__ float4 ld_stream(const float* p) {
   float4 v;

@@ -226,8 +226,8 @@ COS_API int cos_net_synchronize(cos_net* net);
  * reference to 1e-5, not bitwise: set 0 for bit-exact runs), "nvls_unroll",
  * "nvls_p2p" (share of plain-P2P vectors in the NVLS kernel), "train_pipeline"
  * (1 = cos_net_train returns once its batch has left host memory; 0 = after the
- * whole step), "trace" (record %globaltimer at the kernel's phase boundaries),
- * "small_grid" (experimental grid sizing).
+ * whole step), "trace" (record %globaltimer at the kernel's phase boundaries and inside
+ * the two barriers).
  * Read-only via get_option: "resolved_algo", "resolved_kernel", "nvls_active",
  * "transport", "default_grid", "trace_0".."trace_12".  1/0. */
 COS_API int cos_net_set_option(cos_net* net, const char* name, int64_t value);
