@@ -1,6 +1,8 @@
 // caffe_proto_io.cpp -- see caffe_proto_io.hpp.
 #include "caffe_proto_io.hpp"
 
+#include "hdf5_io.hpp"
+
 #include <stdio.h>
 #include <string.h>
 
@@ -225,8 +227,52 @@ bool write_caffemodel(const std::string& path, const std::string& net_name, cons
   return ok;
 }
 
+namespace {
+bool blob_from_h5(const H5Node& d, const std::string& path, ParsedBlob* b, std::string* err) {
+  if (d.kind != H5Node::kFloat32) {
+    *err = "'" + path + "': dataset '" + d.name + "' is not float32";
+    return false;
+  }
+  b->shape = d.shape;
+  b->data = d.f32;
+  return true;
+}
+// datasets "0", "1", ... of a group, in numeric order (the B-tree returns them in strcmp order: "0","1","10","2")
+bool numbered_blobs(const H5Node& g, const std::string& path, std::vector<ParsedBlob>* out, std::string* err) {
+  for (size_t j = 0; j < g.children.size(); ++j) {
+    const H5Node* d = g.find(std::to_string(j));
+    if (!d) {
+      *err = "'" + path + "': group '" + g.name + "' has no dataset '" + std::to_string(j) + "'";
+      return false;
+    }
+    ParsedBlob b;
+    if (!blob_from_h5(*d, path, &b, err)) return false;
+    out->push_back(std::move(b));
+  }
+  return true;
+}
+}  // namespace
+
 bool read_caffemodel(const std::string& path, std::string* net_name, std::vector<ParsedLayer>* layers,
                      std::string* err) {
+  if (h5_is_hdf5(path)) {  // Net::CopyTrainedLayersFromHDF5 (net.cpp:805-851): group "data", one subgroup per layer
+    H5Node root;
+    if (!h5_read(path, &root, err)) return false;
+    const H5Node* data = root.find("data");
+    if (!data || data->kind != H5Node::kGroup) {
+      *err = "'" + path + "' has no 'data' group: not a Caffe HDF5 model";
+      return false;
+    }
+    if (net_name) net_name->clear();
+    for (const auto& L : data->children) {
+      if (L->kind != H5Node::kGroup) continue;
+      ParsedLayer pl;
+      pl.name = L->name;
+      if (!numbered_blobs(*L, path, &pl.blobs, err)) return false;
+      layers->push_back(std::move(pl));
+    }
+    return true;
+  }
   std::vector<unsigned char> buf;
   if (!slurp(path, &buf, err)) return false;
   Reader r{buf.data(), buf.data() + buf.size(), true};
@@ -299,8 +345,57 @@ bool write_solverstate(const std::string& path, int iter, int current_step, cons
   return ok;
 }
 
+bool write_caffemodel_h5(const std::string& path, const std::vector<BlobView>& blobs, std::string* err) {
+  if (!check_views(blobs, err)) return false;
+  H5Node root;
+  H5Node* data = root.add_group("data");
+  H5Node* layer = nullptr;
+  int j = 0;
+  for (size_t i = 0; i < blobs.size(); ++i) {  // consecutive views with one layer_name = that layer's blobs 0, 1, ...
+    if (i == 0 || blobs[i].layer_name != blobs[i - 1].layer_name) {
+      layer = data->add_group(blobs[i].layer_name);
+      j = 0;
+    }
+    std::vector<int64_t> shape = blobs[i].shape;
+    if (shape.empty()) shape.assign(1, static_cast<int64_t>(blobs[i].count));
+    layer->add_float(std::to_string(j++), shape, blobs[i].data, blobs[i].count);
+  }
+  return h5_write(path, root, err);
+}
+
+bool write_solverstate_h5(const std::string& path, int iter, int current_step, const std::string& learned_net,
+                          const std::vector<BlobView>& history, std::string* err) {
+  if (!check_views(history, err)) return false;
+  H5Node root;  // sgd_solver.cpp:288-299
+  root.add_int("iter", iter);
+  root.add_string("learned_net", learned_net);
+  root.add_int("current_step", current_step);
+  H5Node* h = root.add_group("history");
+  for (size_t i = 0; i < history.size(); ++i) {
+    std::vector<int64_t> shape = history[i].shape;
+    if (shape.empty()) shape.assign(1, static_cast<int64_t>(history[i].count));
+    h->add_float(std::to_string(i), shape, history[i].data, history[i].count);
+  }
+  return h5_write(path, root, err);
+}
+
 bool read_solverstate(const std::string& path, int* iter, int* current_step, std::string* learned_net,
                       std::vector<ParsedBlob>* history, std::string* err) {
+  if (h5_is_hdf5(path)) {  // SGDSolver::RestoreSolverStateFromHDF5 (sgd_solver.cpp:325-347)
+    H5Node root;
+    if (!h5_read(path, &root, err)) return false;
+    const H5Node *it = root.find("iter"), *cs = root.find("current_step"), *ln = root.find("learned_net"),
+                 *h = root.find("history");
+    if (!it || it->kind != H5Node::kInt32 || it->i32.empty() || !cs || cs->kind != H5Node::kInt32 || cs->i32.empty() ||
+        !h || h->kind != H5Node::kGroup) {
+      *err = "'" + path + "' is not a SolverState HDF5 file (iter / current_step / history missing)";
+      return false;
+    }
+    if (iter) *iter = it->i32[0];
+    if (current_step) *current_step = cs->i32[0];
+    if (learned_net) *learned_net = (ln && ln->kind == H5Node::kString) ? ln->str : std::string();
+    return numbered_blobs(*h, path, history, err);
+  }
   std::vector<unsigned char> buf;
   if (!slurp(path, &buf, err)) return false;
   Reader r{buf.data(), buf.data() + buf.size(), true};

@@ -51,6 +51,14 @@ bool read_caffemodel(const std::string& path, std::string* net_name, std::vector
 
 bool write_solverstate(const std::string& path, int iter, int current_step, const std::string& learned_net,
                        const std::vector<BlobView>& history, std::string* err);
+
+// snapshot_format: HDF5 (hdf5_io.hpp).  Same content as Net::ToHDF5 (net.cpp:867-917: /data/<layer>/<j> float
+// datasets with the blob's shape) and SGDSolver::SnapshotSolverStateToHDF5 (sgd_solver.cpp:279-301: /iter,
+// /learned_net, /current_step, /history/<i>).  read_caffemodel / read_solverstate recognise HDF5 files by their
+// signature, so restore() works with either format (net.cpp:805-851, sgd_solver.cpp:325-347).
+bool write_caffemodel_h5(const std::string& path, const std::vector<BlobView>& blobs, std::string* err);
+bool write_solverstate_h5(const std::string& path, int iter, int current_step, const std::string& learned_net,
+                          const std::vector<BlobView>& history, std::string* err);
 bool read_solverstate(const std::string& path, int* iter, int* current_step, std::string* learned_net,
                       std::vector<ParsedBlob>* history, std::string* err);
 

@@ -13,6 +13,7 @@
 #include "../../include/caffedistri_b200.h"
 #include "caffe_net.hpp"
 #include "caffe_proto_io.hpp"
+#include "hdf5_io.hpp"
 #include "peer_adapter.hpp"
 #include "solver_spec.hpp"
 
@@ -475,6 +476,64 @@ int cos_solverstate_write(const char* path, int iter, int current_step, const ch
                                  views_from_c(nblobs, nullptr, nullptr, shape_ndims, dims_flat, data), &err))
       return fail(err);
     return 1;
+  })
+}
+
+int cos_caffemodel_write_h5(const char* path, int nblobs, const char* const* layer_names, const int* shape_ndims,
+                            const int64_t* dims_flat, const float* const* data) {
+  COS_GUARD(0, {
+    if (!path || nblobs < 0 || (nblobs && (!layer_names || !shape_ndims || !dims_flat || !data)))
+      return fail("bad argument");
+    std::string err;
+    if (!cosb::write_caffemodel_h5(path, views_from_c(nblobs, layer_names, nullptr, shape_ndims, dims_flat, data), &err))
+      return fail(err);
+    return 1;
+  })
+}
+
+int cos_solverstate_write_h5(const char* path, int iter, int current_step, const char* learned_net, int nblobs,
+                             const int* shape_ndims, const int64_t* dims_flat, const float* const* data) {
+  COS_GUARD(0, {
+    if (!path || nblobs < 0 || (nblobs && (!shape_ndims || !dims_flat || !data))) return fail("bad argument");
+    std::string err;
+    if (!cosb::write_solverstate_h5(path, iter, current_step, learned_net ? learned_net : "",
+                                    views_from_c(nblobs, nullptr, nullptr, shape_ndims, dims_flat, data), &err))
+      return fail(err);
+    return 1;
+  })
+}
+
+int64_t cos_hdf5_read_dataset(const char* path, const char* dataset, int64_t* dims, int max_dims, int* ndims, float* out,
+                              int64_t cap) {
+  COS_GUARD(-1, {
+    if (!path || !dataset) return fail("bad argument", -1);
+    cosb::H5Node root;
+    std::string err;
+    if (!cosb::h5_read(path, &root, &err)) return fail(err, -1);
+    const cosb::H5Node* n = &root;
+    std::string rest = dataset;
+    while (!rest.empty()) {
+      if (rest[0] == '/') {
+        rest.erase(0, 1);
+        continue;
+      }
+      const size_t slash = rest.find('/');
+      const std::string part = rest.substr(0, slash);
+      n = n->find(part);
+      if (!n) return fail(std::string("no object '") + dataset + "' in '" + path + "'", -1);
+      rest = slash == std::string::npos ? "" : rest.substr(slash + 1);
+    }
+    if (n->kind != cosb::H5Node::kFloat32 && n->kind != cosb::H5Node::kInt32)
+      return fail(std::string("'") + dataset + "' is not a numeric dataset", -1);
+    if (ndims) *ndims = static_cast<int>(n->shape.size());
+    for (int i = 0; dims && i < max_dims && i < static_cast<int>(n->shape.size()); ++i) dims[i] = n->shape[i];
+    const int64_t cnt = static_cast<int64_t>(n->count);
+    if (out && cap >= cnt) {
+      if (n->kind == cosb::H5Node::kFloat32) memcpy(out, n->f32.data(), cnt * sizeof(float));
+      else
+        for (int64_t i = 0; i < cnt; ++i) out[i] = static_cast<float>(n->i32[i]);
+    }
+    return cnt;
   })
 }
 

@@ -156,10 +156,11 @@ COS_API int cos_net_get_test_interval(cos_net* net);
 
 /* J:171 snapshot / JN:537-548, CN:735-738 -> Solver::Snapshot (solver.cpp:400-425):
  * writes stock-Caffe binaryproto files <prefix>_iter_<n>.caffemodel (NetParameter)
- * and .solverstate (SolverState) and returns the iteration, -1 on failure.  A solver
- * asking for snapshot_format: HDF5 (sgd_solver.cpp:279-323) trains normally but its
- * snapshot() fails with a clear error: there is no HDF5 writer here, and binaryproto
- * content under ".h5" names would break every stock reader.  Called on rank 0 only, like
+ * and .solverstate (SolverState) and returns the iteration, -1 on failure.  With
+ * snapshot_format: HDF5 (sgd_solver.cpp:279-323, net.cpp:867-917) the files are
+ * <prefix>_iter_<n>.caffemodel.h5 / .solverstate.h5 in HDF5's original file layout,
+ * written without libhdf5 (csrc/hdf5_io.cpp): /data/<layer>/<j>, /iter, /learned_net,
+ * /current_step, /history/<i>.  Called on rank 0 only, like
  * the reference (CaffeProcessor.scala:454-465); NOT collective: the history
  * shards of the other ranks are read through their mapped arenas. */
 COS_API int cos_net_snapshot(cos_net* net);
@@ -279,6 +280,18 @@ COS_API int64_t cos_solverstate_read(const char* path, int* iter, int* current_s
                                      int learned_cap, int blob_index, float* out, int64_t cap);
 
 /* -------------------------- host helpers (pure functions, no device) ------ */
+/* HDF5 twins of the two writers above (snapshot_format: HDF5).  cos_caffemodel_read / cos_solverstate_read
+ * recognise HDF5 files by their signature, so they read either format. */
+COS_API int cos_caffemodel_write_h5(const char* path, int nblobs, const char* const* layer_names, const int* shape_ndims,
+                                    const int64_t* dims_flat, const float* const* data);
+COS_API int cos_solverstate_write_h5(const char* path, int iter, int current_step, const char* learned_net, int nblobs,
+                                     const int* shape_ndims, const int64_t* dims_flat, const float* const* data);
+/* One dataset of ANY old-style HDF5 file by absolute path ("/data", "/history/3"): returns the element count
+ * (float32 copied, int32 converted to float), fills up to max_dims dims and *ndims; -1 on failure.  Used to pin the
+ * reader on libhdf5-written files. */
+COS_API int64_t cos_hdf5_read_dataset(const char* path, const char* dataset, int64_t* dims, int max_dims, int* ndims,
+                                      float* out, int64_t cap);
+
 COS_API void cos_chunk(uint64_t param_count, int cluster_size, int peer, uint64_t* offs, uint64_t* size);
 COS_API float cos_learning_rate(const char* lr_policy, float base_lr, float gamma, float power, int stepsize,
                                 const int* stepvalues, int nstepvalues, int max_iter, int iter,

@@ -208,24 +208,55 @@ def test_snapshot_restore_resumes_bit_exactly(cos, oracle, tmp_path):
         c.deallocate()
 
 
-def test_hdf5_snapshot_format_trains_but_refuses_to_snapshot(cos, tmp_path):
-    """The reference's own cifar10_quick_solver.prototxt asks for snapshot_format: HDF5.  Such a solver must
-    load and train; snapshot() must fail loudly (no HDF5 writer here) instead of writing binaryproto content
-    under the .h5 names CaffeNet.java:203-205 computes."""
+def test_hdf5_snapshot_and_resume(cos, oracle, tmp_path):
+    """The reference's own cifar10_quick_solver.prototxt asks for snapshot_format: HDF5 (solver.cpp:417-418,
+    sgd_solver.cpp:251-252,279-301, net.cpp:867-917).  snapshot() then writes <prefix>_iter_<n>.caffemodel.h5 /
+    .solverstate.h5 (the names CaffeNet.java:203-205 computes) as real HDF5 (csrc/hdf5_io.cpp), and a new net
+    resumed from them continues bit-exactly (RestoreSolverStateFromHDF5 / CopyTrainedLayersFromHDF5)."""
     from caffeonspark_b200 import nets
+    from gpu_util import to_dev, to_host
+    import torch
     (tmp_path / "net.prototxt").write_text(nets.net_prototxt("cifar10_quick"))
     (tmp_path / "solver.prototxt").write_text(
-        f'net: "net.prototxt"\nbase_lr: 0.001\nmomentum: 0.9\nweight_decay: 0.004\nlr_policy: "fixed"\n'
-        f'max_iter: 10\nsnapshot_format: HDF5\nsnapshot_prefix: "{tmp_path / "c10"}"\n')
-    net = cos.CaffeNet(str(tmp_path / "solver.prototxt"))
+        f'net: "net.prototxt"\nbase_lr: 0.001\nmomentum: 0.9\nweight_decay: 0.004\nlr_policy: "step"\ngamma: 0.5\n'
+        f'stepsize: 2\nmax_iter: 10\nsnapshot_format: HDF5\nsnapshot_prefix: "{tmp_path / "c10"}"\n')
+    solver = str(tmp_path / "solver.prototxt")
+    P = nets.EXPECTED_PARAM_COUNT["cifar10_quick"]
+    grads = [oracle.fill(P, 23, 4096 * (t + 1), 0.01) for t in range(4)]
+
+    def run_steps(net, ts):
+        for t in ts:
+            to_dev(net.diff(), grads[t])
+            torch.cuda.synchronize()
+            assert net.sync_step(0) and net.synchronize(), net.last_error()
+
+    a = cos.CaffeNet(solver)
     try:
-        assert net.connect(net.localAddresses())
-        assert net.sync_step(0) and net.synchronize()
-        assert net.snapshotFilename(1, False).endswith("_iter_1.caffemodel.h5")
-        assert net.snapshot() == -1 and "HDF5 is not supported" in net.last_error()
-        assert not list(tmp_path.glob("c10_iter_*"))
+        assert a.connect(a.localAddresses())
+        to_dev(a.data(), oracle.fill(P, 23, 0, 0.05))
+        run_steps(a, [0, 1, 2])
+        assert a.snapshot() == 3, a.last_error()
+        model, state = a.snapshotFilename(3, False), a.snapshotFilename(3, True)
+        assert model.endswith("c10_iter_3.caffemodel.h5") and state.endswith("c10_iter_3.solverstate.h5")
+        assert open(model, "rb").read(8) == b"\x89HDF\r\n\x1a\n" and open(state, "rb").read(8) == b"\x89HDF\r\n\x1a\n"
+        w3 = to_host(a.data())
+        run_steps(a, [3])
+        w_ref, h_ref = to_host(a.data()), to_host(a.history())
     finally:
-        net.deallocate()
+        a.deallocate()
+    assert cos.read_caffemodel_blob(model, "conv1", 0).size == 2400        # /data/conv1/0
+    it, step, learned, hist = cos.read_solverstate(state)
+    assert (it, step, learned) == (3, 1, model) and len(hist) == 10
+    b = cos.CaffeNet(solver, "", state)  # Solver::Restore follows learned_net for the weights
+    try:
+        assert b.connect(b.localAddresses())
+        assert b.iter() == 3
+        assert_bits_equal(to_host(b.data()), w3, "weights restored from the .caffemodel.h5")
+        run_steps(b, [3])
+        assert_bits_equal(to_host(b.data()), w_ref, "weights after resuming from HDF5")
+        assert_bits_equal(to_host(b.history()), h_ref, "history after resuming from HDF5")
+    finally:
+        b.deallocate()
 
 
 def test_device_fill_is_the_oracles_generator(cos, oracle):
