@@ -392,6 +392,7 @@ struct Reader {
     const uint64_t want = n->kind == H5Node::kString ? count * esize : count * 4;
     n->count = count;
     if (addr == kUndef || want == 0) {  // never written: zeros / empty
+      if (count > (1ull << 28)) return fail("dataset '" + n->name + "' has no data but claims " + std::to_string(count) + " elements");
       if (n->kind == H5Node::kFloat32) n->f32.assign(count, 0.f);
       else if (n->kind == H5Node::kInt32) n->i32.assign(count, 0);
       return true;

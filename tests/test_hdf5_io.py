@@ -261,3 +261,31 @@ def test_truncated_and_foreign_hdf5_is_rejected(cos, tmp_path):
     many = [np.zeros(1, np.float32)] * 300
     assert _write_model(L, str(tmp_path / "many.h5"), many, [f"l{i}" for i in range(300)]) == 0
     assert b"256 links" in L.cos_last_error()
+
+
+def test_reader_never_crashes_on_mutated_files(cos, tmp_path):
+    """Bounds checks: random byte mutations / truncations of a valid file must yield an error or a (different) parse,
+    never a crash, a hang or an over-read (the reader slurps the file and checks every offset against its size)."""
+    from caffeonspark_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(7)
+    arrays = [rng.randn(4, 3).astype(np.float32), rng.randn(4).astype(np.float32), rng.randn(5).astype(np.float32)]
+    path = str(tmp_path / "seed.caffemodel.h5")
+    assert _write_model(L, path, arrays, ["ip1", "ip1", "ip2"])
+    raw = bytearray(open(path, "rb").read())
+    meta_end = 4000  # object headers, B-trees, heaps and symbol nodes live in the first few KB
+    p = tmp_path / "mut.h5"
+    outcomes = set()
+    for trial in range(400):
+        m = bytearray(raw)
+        for _ in range(int(rng.randint(1, 6))):
+            pos = int(rng.randint(8, min(len(m), meta_end)))
+            m[pos] = int(rng.randint(0, 256)) if rng.rand() < 0.7 else (0xff if rng.rand() < 0.5 else 0x00)
+        if rng.rand() < 0.1:
+            m = m[:int(rng.randint(8, len(m)))]
+        p.write_bytes(bytes(m))
+        n = L.cos_caffemodel_read(str(p).encode(), b"ip1", 0, None, 0)
+        outcomes.add(n)
+        it, step = ctypes.c_int(), ctypes.c_int()
+        L.cos_solverstate_read(str(p).encode(), ctypes.byref(it), ctypes.byref(step), None, 0, -1, None, 0)
+    assert -1 in outcomes and 12 in outcomes  # some mutations are fatal, some are harmless
